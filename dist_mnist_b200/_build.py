@@ -1,0 +1,110 @@
+"""In-tree build of the native runtime (`libdmnist_sm100a.so`).
+
+Every CUDA source is compiled for sm_100a only
+(`-gencode arch=compute_100a,code=sm_100a -lineinfo`); nvcc cross-compiles without a GPU, so this
+runs on the CPU build box. The shared object lands next to this file so it travels to GPU boxes
+with the source snapshot (a JIT cache under ~/.cache would not).
+
+    python -m dist_mnist_b200._build [--force] [--verbose]
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+BUILD_DIR = PKG_DIR.parent / "build" / "native"
+LIB_NAME = "libdmnist_sm100a.so"
+LIB_PATH = PKG_DIR / LIB_NAME
+
+CUDA_SOURCES = ["gemm_sm100.cu", "head_sm100.cu", "ps_apply_sm100.cu", "p2p_sm100.cu", "executor.cu", "api.cu"]
+CXX_SOURCES = ["host_runtime.cpp"]
+HEADERS = ["common.cuh", "protocol.h"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+    "-diag-suppress", "550",
+]
+CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall"]
+
+
+def _cuda_home() -> Path:
+    for cand in (os.environ.get("CUDA_HOME"), os.environ.get("CUDA_PATH"), "/usr/local/cuda"):
+        if cand and (Path(cand) / "bin" / "nvcc").exists():
+            return Path(cand)
+    nvcc = shutil.which("nvcc")
+    if nvcc:
+        return Path(nvcc).resolve().parent.parent
+    raise RuntimeError("nvcc not found (set CUDA_HOME)")
+
+
+def _stale(target: Path, deps: list[Path]) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def _run(cmd: list[str], verbose: bool) -> None:
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"command failed ({res.returncode}): {' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
+    if verbose and (res.stdout or res.stderr):
+        print(res.stdout, res.stderr, flush=True)
+
+
+def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> Path:
+    """Compile (if stale) and return the path of the shared object."""
+    cuda = _cuda_home()
+    nvcc = str(cuda / "bin" / "nvcc")
+    BUILD_DIR.mkdir(parents=True, exist_ok=True)
+    headers = [CSRC / h for h in HEADERS]
+    jobs = []
+    objs: list[Path] = []
+    for src in CUDA_SOURCES:
+        s = CSRC / src
+        o = BUILD_DIR / (s.stem + ".o")
+        objs.append(o)
+        if force or _stale(o, [s, *headers, Path(__file__)]):
+            flags = list(NVCC_FLAGS) + (["-Xptxas", "-v"] if ptxas_info else [])
+            jobs.append([nvcc, *flags, "-I", str(CSRC), "-c", str(s), "-o", str(o)])
+    for src in CXX_SOURCES:
+        s = CSRC / src
+        o = BUILD_DIR / (s.stem + ".o")
+        objs.append(o)
+        if force or _stale(o, [s, *headers, Path(__file__)]):
+            jobs.append(["g++", *CXX_FLAGS, "-I", str(CSRC), "-c", str(s), "-o", str(o)])
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+            list(ex.map(lambda c: _run(c, verbose or ptxas_info), jobs))
+    if force or jobs or _stale(LIB_PATH, objs):
+        tmp = LIB_PATH.with_suffix(".so.tmp")
+        _run(
+            [nvcc, "-shared", "-cudart", "shared", "-o", str(tmp), *map(str, objs),
+             "-Xlinker", f"-rpath={cuda / 'lib64'}", "-lpthread", "-lrt"],
+            verbose,
+        )
+        os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+def main(argv: list[str]) -> int:
+    force = "--force" in argv
+    verbose = "--verbose" in argv
+    path = build(force=force, verbose=verbose, ptxas_info="--ptxas-info" in argv)
+    print(f"built {path} ({path.stat().st_size} bytes)")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main(sys.argv[1:]))

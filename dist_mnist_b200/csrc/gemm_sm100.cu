@@ -1,0 +1,301 @@
+// tcgen05 / TMEM / TMA dense-layer GEMM for sm_100a, with the parameter-server transfers fused in.
+//
+//   D[M, N] (fp32, TMEM) = A[M, K] * B[N, K]^T            one 128 x bn output tile per CTA
+//
+// Operand roles in the MLP (all tensors keep their natural row-major layout; no transposes):
+//   forward   : A = W[out][in]   (K-major, *pulled straight from the PS shard over NVLink by TMA*)
+//               B = x[batch][in] (K-major)          D = pre-activation^T      -> EPI_TRANSPOSED (+bias, relu)
+//   dW        : A = dy[batch][out] (MN-major)  B = x[batch][in] (MN-major)   reduction over batch
+//               D = dW[out][in]                     -> EPI_ROWMAJOR_PUSH: the epilogue *is* the gradient
+//               push (P2P stores into the PS mailbox + release flag, or red.add for async SGD)
+//   dX        : A = W[out][in] (MN-major, pulled from the PS)  B = dy[batch][out] (K-major)
+//               D = dx^T                            -> EPI_TRANSPOSED (* relu' mask, bias-grad sums)
+//
+// Reference parity: these replace the MatMul/BiasAdd/Relu (+grads) ops of
+// /root/reference/distributed_server-basic.py:49-52,103 and the implicit gRPC variable
+// fetch / gradient send around them (SURVEY.md K1,K2,K6,X3,X4).
+//
+// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+#include "common.cuh"
+#include "protocol.h"
+
+namespace dm {
+
+constexpr int kGemmThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kABytes = kTileM * 128;  // one A stage: 128 rows x 128 B (K-major) or slabs x BK rows x 128 B
+
+// Resolve a push target for the current sequence number: returns the destination base pointer
+// (slot applied) and the flag array for that slot.
+struct ResolvedPush {
+  float* base;
+  uint32_t* flags;
+  uint32_t seq;
+};
+__device__ __forceinline__ ResolvedPush resolve_push(const PushTarget& t) {
+  ResolvedPush r;
+  r.seq = t.seq_ptr ? *reinterpret_cast<const volatile uint32_t*>(t.seq_ptr) : 1u;
+  r.base = t.base;
+  r.flags = t.flags;
+  if (t.mode == PUSH_MAILBOX) {
+    const uint32_t slot = r.seq % t.nslots;
+    r.base = t.base + static_cast<uint64_t>(slot) * t.slot_stride;
+    r.flags = t.flags + static_cast<uint64_t>(slot) * t.flag_slot_stride;
+  }
+  return r;
+}
+
+template <typename T, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  constexpr int BKE = 128 / sizeof(T);     // k elements per stage chunk (32 tf32 / 64 bf16) == 128 bytes
+  constexpr int UMMA_K = 32 / sizeof(T);   // 8 / 16
+  constexpr int KSTEPS = BKE / UMMA_K;     // 4
+  constexpr int SLAB = BKE;                // MN-major: elements per 128-byte wide slab
+  // MN-major 32-bit (tf32) operands must use the 32-byte-chunk swizzle (SWIZZLE_128B_BASE32B: atoms of
+  // 4 k-rows x 128 B, TMA mode 128B_ATOM_32B); 16-bit MN-major and every K-major operand use plain SWIZZLE_128B.
+  constexpr bool MN32 = sizeof(T) == 4;
+  constexpr uint32_t MN_LAYOUT = MN32 ? 1u : 2u;
+  constexpr uint32_t MN_SBO = MN32 ? 512u : 1024u;
+
+  const int bn = p.bn;
+  const int b_bytes = bn * 128;
+  const int stage_bytes = kABytes + b_bytes;
+  const int stages = p.stages;
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tmem_full_bar = empty_bar + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kTileM;
+  const int n0 = blockIdx.y * bn;
+  const int kc_total = (p.K + BKE - 1) / BKE;
+  const int kc_begin = blockIdx.z * p.kc_per_split;
+  const int kc_end = min(kc_total, kc_begin + p.kc_per_split);
+  const int nkc = kc_end - kc_begin;
+
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(bn)) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    // The first kernel of a training step opens a new push sequence number (it does not read it itself;
+    // every later kernel of the step does, after this kernel has completed).
+    if (p.bump_seq != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *p.bump_seq += 1;
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < stages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, tmem_cols);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int i = 0; i < nkc; ++i) {
+        const int s = i % stages;
+        const uint32_t ph = (i / stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+        const int k0 = (kc_begin + i) * BKE;
+        uint8_t* sa = smem + s * stage_bytes;
+        uint8_t* sb = sa + kABytes;
+        if constexpr (!A_MN) {
+          tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box {BKE, 128}
+        } else {
+#pragma unroll
+          for (int slab = 0; slab < kTileM / SLAB; ++slab)  // box {SLAB, BKE}: BKE k-rows of 128 B
+            tma_load_2d(sa + slab * (BKE * 128), &tmA, &full_bar[s], m0 + slab * SLAB, k0);
+        }
+        if constexpr (!B_MN) {
+          tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);  // box {BKE, bn}
+        } else {
+          for (int slab = 0; slab < bn / SLAB; ++slab)
+            tma_load_2d(sb + slab * (BKE * 128), &tmB, &full_bar[s], n0 + slab * SLAB, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one elected lane) =====================
+    const uint32_t idesc = make_idesc(MmaKind<T>::kFormat, A_MN, B_MN, kTileM, bn);
+    for (int i = 0; i < nkc; ++i) {
+      const int s = i % stages;
+      const uint32_t ph = (i / stages) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+        const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+        for (int j = 0; j < KSTEPS; ++j) {
+          // K-major : advance 32 B inside the 128 B swizzle atom; SBO = 1024 (8 rows x 128 B)
+          // MN-major: advance UMMA_K k-rows (x 128 B); LBO = slab stride, SBO = k-group stride (8 rows, or 4 for tf32)
+          const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_addr + j * (UMMA_K * 128), BKE * 128, MN_SBO, MN_LAYOUT)
+                                      : make_smem_desc_sw128(a_addr + j * 32, 16, 1024);
+          const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_addr + j * (UMMA_K * 128), BKE * 128, MN_SBO, MN_LAYOUT)
+                                      : make_smem_desc_sw128(b_addr + j * 32, 16, 1024);
+          MmaKind<T>::mma(tmem_base, adesc, bdesc, idesc, (i > 0 || j > 0) ? 1u : 0u);
+        }
+        tcgen05_commit(&empty_bar[s]);
+        if (i == nkc - 1) tcgen05_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue warps (TMEM -> registers -> global / peer) =====================
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    const bool m_ok = m < p.M;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+    if (p.epi == EPI_TRANSPOSED) {
+      const float bias = (p.bias != nullptr && m_ok) ? p.bias[m] : 0.f;
+      float colsum = 0.f;
+      for (int c0 = 0; c0 < bn; c0 += 16) {
+        float v[16];
+        tmem_ld_32x32b_x16(taddr + c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = n0 + c0 + j;
+          if (n < p.N && m_ok) {
+            float val = v[j] + bias;
+            if (p.relu) val = fmaxf(val, 0.f);
+            if (p.mask != nullptr) {
+              const float a = p.mask_bf16
+                                  ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(
+                                        p.mask)[static_cast<size_t>(n) * p.ldmask + m])
+                                  : reinterpret_cast<const float*>(p.mask)[static_cast<size_t>(n) * p.ldmask + m];
+              val = a > 0.f ? val : 0.f;
+            }
+            colsum += val;
+            const size_t o = static_cast<size_t>(n) * p.ldo + m;
+            if (blockIdx.z == 0 && gridDim.z == 1) {
+              if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(val);
+              else reinterpret_cast<float*>(p.out)[o] = val;
+            } else {
+              atomicAdd(reinterpret_cast<float*>(p.out) + o, v[j]);  // split-K partials (fp32 out, no bias/act)
+            }
+          }
+        }
+      }
+      if (p.has_colsum) {
+        // bias gradient: this lane owns feature m and has just summed it over the whole batch tile.
+        const ResolvedPush r = resolve_push(p.colsum);
+        if (m_ok) {
+          float* dst = r.base + p.colsum_offset + m;
+          if (p.colsum.mode == PUSH_ATOMIC) red_add_sys_f32(dst, p.colsum.scale * colsum);
+          else if (gridDim.y > 1) atomicAdd(dst, colsum);
+          else *dst = colsum;
+        }
+        if (p.colsum.mode == PUSH_MAILBOX) {
+          __threadfence_system();
+          named_bar_sync(1, 128);
+          if (threadIdx.x == 64) st_release_sys_u32(r.flags + p.colsum_item_base + blockIdx.x, r.seq);
+        }
+      }
+    } else {
+      // EPI_ROWMAJOR_PUSH: lane m owns row m of dW; push bn consecutive columns starting at n0.
+      const ResolvedPush r = resolve_push(p.push);
+      float* row = r.base + p.push_offset + static_cast<size_t>(m) * p.ldo + n0;
+      const bool vec_ok = ((p.ldo & 3) == 0) && ((p.push_offset & 3) == 0);
+      for (int c0 = 0; c0 < bn; c0 += 16) {
+        float v[16];
+        tmem_ld_32x32b_x16(taddr + c0, v);
+        if (!m_ok) continue;
+        const int n = n0 + c0;
+        if (p.push.mode == PUSH_ATOMIC) {
+          const float sc = p.push.scale;
+          if (vec_ok && n + 16 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              red_add_sys_v4f32(row + c0 + j, sc * v[j], sc * v[j + 1], sc * v[j + 2], sc * v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n + j < p.N) red_add_sys_f32(row + c0 + j, sc * v[j]);
+          }
+        } else {
+          if (vec_ok && n + 16 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) st_global_v4f32(row + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n + j < p.N) row[c0 + j] = v[j];
+          }
+        }
+      }
+      if (p.push.mode == PUSH_MAILBOX) {
+        // make this tile's P2P stores visible at system scope, then publish the tile's flag.
+        __threadfence_system();
+        named_bar_sync(1, 128);
+        if (threadIdx.x == 64)
+          st_release_sys_u32(r.flags + p.push_item_base + blockIdx.x * gridDim.y + blockIdx.y, r.seq);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+size_t gemm_smem_bytes(int bn, int stages) {
+  return static_cast<size_t>(stages) * (kABytes + bn * 128) + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+}
+
+template <typename T, bool A_MN, bool B_MN>
+static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, dim3 grid,
+                              cudaStream_t stream) {
+  auto kern = gemm_tcgen05_kernel<T, A_MN, B_MN>;
+  const size_t smem = gemm_smem_bytes(p.bn, p.stages);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p);
+  return cudaGetLastError();
+}
+
+// dtype: 0 = fp32 (tf32 MMA), 1 = bf16
+cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int dtype,
+                        bool a_mn, bool b_mn, int splits, cudaStream_t stream) {
+  dim3 grid((p.M + kTileM - 1) / kTileM, (p.N + p.bn - 1) / p.bn, splits);
+#define DM_DISPATCH(T)                                                                  \
+  if (!a_mn && !b_mn) return launch_one<T, false, false>(tmA, tmB, p, grid, stream);   \
+  if (a_mn && b_mn) return launch_one<T, true, true>(tmA, tmB, p, grid, stream);       \
+  if (a_mn && !b_mn) return launch_one<T, true, false>(tmA, tmB, p, grid, stream);     \
+  return launch_one<T, false, true>(tmA, tmB, p, grid, stream);
+  if (dtype == 0) {
+    DM_DISPATCH(float)
+  } else {
+    DM_DISPATCH(__nv_bfloat16)
+  }
+#undef DM_DISPATCH
+}
+
+}  // namespace dm

@@ -1,0 +1,326 @@
+// Fused classifier head for sm_100a: last dense layer + softmax + loss + accuracy + every gradient that
+// does not need a big GEMM, with the small-variable gradient push fused in.
+//
+// One launch computes, for h = activations of the last hidden layer [B][H]:
+//   logits = h . W_last^T + b_last              (W_last/b_last read straight from the PS shard: peer loads)
+//   p      = softmax(logits)
+//   loss   = LOSS_BOOK: -mean_{B x C}(labels * log(clip(p, 1e-10, 1)))     reference DS:52-53
+//            LOSS_XENT: mean_B(softmax_cross_entropy_with_logits)           reference DS:35
+//   correct= #(argmax logits == argmax labels)                              (accuracy numerator)
+//   dlogits, dW_last = dlogits^T . h, db_last = sum_B dlogits
+//   dpre   = (dlogits . W_last) * relu'(h)      -> [B][H] buffer consumed by the tcgen05 dW / dX GEMMs
+//   db_hid = sum_B dpre
+// and pushes dW_last / db_last / db_hid to the parameter server (mailbox + flags, or red.add for SGD).
+//
+// grid = ceil(H / 128) CTAs x 256 threads. Every CTA recomputes the (tiny) logits/softmax phase and then
+// owns a 128-wide slice of H for the gradient phase, so no inter-CTA synchronisation is needed.
+// Replaces reference ops DS:52-53 + their gradients from DS:103 (part of K6, K12).
+#include "common.cuh"
+#include "protocol.h"
+
+namespace dm {
+
+constexpr int kHeadThreads = 256;
+constexpr int kHeadSlice = 128;
+constexpr int kMaxC = 16;
+constexpr int kMaxB = 256;
+
+__device__ __forceinline__ float ld_act(const void* p, size_t idx, int is_bf16) {
+  return is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[idx])
+                 : reinterpret_cast<const float*>(p)[idx];
+}
+__device__ __forceinline__ void st_act(void* p, size_t idx, int is_bf16, float v) {
+  if (is_bf16) reinterpret_cast<__nv_bfloat16*>(p)[idx] = __float2bfloat16(v);
+  else reinterpret_cast<float*>(p)[idx] = v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct ResolvedPushH {
+  float* base;
+  uint32_t* flags;
+};
+__device__ __forceinline__ ResolvedPushH resolve_push_h(const PushTarget& t, uint32_t seq) {
+  ResolvedPushH r{t.base, t.flags};
+  if (t.mode == PUSH_MAILBOX) {
+    const uint32_t slot = seq % t.nslots;
+    r.base = t.base + static_cast<uint64_t>(slot) * t.slot_stride;
+    r.flags = t.flags + static_cast<uint64_t>(slot) * t.flag_slot_stride;
+  }
+  return r;
+}
+__device__ __forceinline__ void push_value(const PushTarget& t, float* dst, float v) {
+  if (t.mode == PUSH_ATOMIC) red_add_sys_f32(dst, t.scale * v);
+  else *dst = v;
+}
+
+__global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_constant__ HeadParams p) {
+  extern __shared__ float hsm[];
+  // smem carve-up
+  float* sW = hsm;                         // [C][H]
+  float* sLogit = sW + p.C * p.H;          // [B][kMaxC]  logits -> dlogits
+  float* sRed = sLogit + p.B_pad * kMaxC;  // [32] block reductions
+  float* sPart = sRed + 64;                // [2][kHeadSlice][kMaxC + 1] dW/db partials of the second b-half
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int C = p.C, H = p.H, B = p.B;
+
+  __shared__ uint32_t s_seq;
+  __shared__ uint32_t s_gstep;
+  if (tid == 0) {
+    uint32_t seq = p.seq_ptr ? *reinterpret_cast<volatile uint32_t*>(p.seq_ptr) : 1u;
+    s_seq = seq;
+    uint32_t gstep = seq;
+    if (p.compute_grads && p.push.mode == PUSH_MAILBOX && p.inbox != nullptr) {
+      // flow control: the mailbox slot we are about to overwrite was used by push (seq - nslots);
+      // wait until the PS has acknowledged it. The PS writes the inbox into *our* HBM, so this spins locally.
+      const volatile uint32_t* inbox = reinterpret_cast<const volatile uint32_t*>(p.inbox);
+      if (seq > p.nslots) {
+        const uint64_t t0 = globaltimer_ns();
+        for (uint32_t i = 0; i < p.n_inbox; ++i) {
+          while (static_cast<int32_t>(inbox[2 * i] - (seq - p.nslots)) < 0) {
+            if (globaltimer_ns() - t0 > DM_SPIN_TIMEOUT_NS) {
+              printf("[dm] head: PS %u ack timeout (seq=%u ack=%u)\n", i, seq, inbox[2 * i]);
+              __trap();
+            }
+          }
+        }
+      }
+      gstep = inbox[1];  // shard 0 owns global_step (reference: first variable created, DS:91)
+    }
+    s_gstep = gstep;
+  }
+
+  // ---- phase 1: W_last -> smem, logits for every row (each CTA recomputes; it is tiny) ----
+  for (int i = tid; i < C * H; i += kHeadThreads) sW[i] = p.w_last[i];
+  __syncthreads();
+  const uint32_t seq = s_seq;
+
+  for (int b = warp; b < B; b += kHeadThreads / 32) {
+    float acc[kMaxC];
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) acc[c] = 0.f;
+    for (int h = lane; h < H; h += 32) {
+      const float hv = ld_act(p.h, static_cast<size_t>(b) * p.ldh + h, p.act_bf16);
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c)
+        if (c < C) acc[c] = fmaf(hv, sW[c * H + h], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) {
+      const float s = warp_sum(acc[c]);
+      if (lane == 0 && c < C) sLogit[b * kMaxC + c] = s + p.b_last[c];
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: softmax / loss / accuracy / dlogits, one thread per row ----
+  float loss_part = 0.f;
+  float corr_part = 0.f;
+  for (int b = tid; b < B; b += kHeadThreads) {
+    float z[kMaxC], y[kMaxC];
+    float zmax = -INFINITY, ysum = 0.f;
+    int zarg = 0, yarg = 0;
+    float ybest = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) {
+      if (c < C) {
+        z[c] = sLogit[b * kMaxC + c];
+        y[c] = p.labels[static_cast<size_t>(b) * C + c];
+        if (z[c] > zmax) { zmax = z[c]; zarg = c; }
+        if (y[c] > ybest) { ybest = y[c]; yarg = c; }
+        ysum += y[c];
+      }
+    }
+    float esum = 0.f;
+    float e[kMaxC];
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c)
+      if (c < C) { e[c] = __expf(z[c] - zmax); esum += e[c]; }
+    const float inv = 1.f / esum;
+    corr_part += (zarg == yarg) ? 1.f : 0.f;
+    if (p.loss_kind == LOSS_BOOK) {
+      // L = -(1/(B*C)) sum y*log(clip(p,1e-10,1));  dL/dp = -y/(B*C*p) where the clip passes gradient
+      const float k = 1.f / (static_cast<float>(B) * static_cast<float>(C));
+      float g[kMaxC];
+      float gp = 0.f;
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c) {
+        if (c < C) {
+          const float pc = e[c] * inv;
+          const float pcl = fminf(fmaxf(pc, 1e-10f), 1.0f);
+          loss_part -= k * y[c] * __logf(pcl);
+          const bool pass = (pc >= 1e-10f) && (pc <= 1.0f);
+          g[c] = pass ? (-k * y[c] / pc) : 0.f;
+          gp += g[c] * pc;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c)
+        if (c < C) { const float pc = e[c] * inv; sLogit[b * kMaxC + c] = pc * (g[c] - gp); }
+    } else {
+      // L = (1/B) sum_b -sum_c y*log_softmax(z);  dz = (p*sum(y) - y)/B
+      const float k = 1.f / static_cast<float>(B);
+      const float lse = zmax + __logf(esum);
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c) {
+        if (c < C) {
+          loss_part -= k * y[c] * (z[c] - lse);
+          sLogit[b * kMaxC + c] = k * (e[c] * inv * ysum - y[c]);
+        }
+      }
+    }
+  }
+  // block-reduce loss / correct (only CTA 0 reports them)
+  loss_part = warp_sum(loss_part);
+  corr_part = warp_sum(corr_part);
+  if (lane == 0) { sRed[warp] = loss_part; sRed[32 + warp] = corr_part; }
+  __syncthreads();
+  if (blockIdx.x == 0 && tid == 0) {
+    float l = 0.f, cr = 0.f;
+    for (int w = 0; w < kHeadThreads / 32; ++w) { l += sRed[w]; cr += sRed[32 + w]; }
+    uint32_t gstep = s_gstep;
+    if (p.compute_grads && p.push.mode == PUSH_ATOMIC && p.ps_global_step != nullptr)
+      gstep = atom_add_sys_u32(p.ps_global_step, 1u) + 1u;  // async SGD: this push *is* global step gstep
+    StepResult r;
+    r.loss = l;
+    r.global_step = gstep;
+    r.correct = static_cast<uint32_t>(cr + 0.5f);
+    r.seq = seq;
+    *p.result = r;
+  }
+  if (!p.compute_grads) return;
+
+  // ---- phase 3: gradients for this CTA's 128-wide slice of H ----
+  const int hh = tid & (kHeadSlice - 1);
+  const int half = tid >> 7;  // two halves split the batch rows
+  const int h = blockIdx.x * kHeadSlice + hh;
+  const bool h_ok = h < H;
+  float wcol[kMaxC], dw[kMaxC];
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c) { wcol[c] = (h_ok && c < C) ? sW[c * H + h] : 0.f; dw[c] = 0.f; }
+  float dbh = 0.f;
+  const int bhalf = (B + 1) / 2;
+  const int b_lo = half == 0 ? 0 : bhalf;
+  const int b_hi = half == 0 ? bhalf : B;
+  for (int b = b_lo; b < b_hi; ++b) {
+    float hv = 0.f;
+    if (h_ok) hv = ld_act(p.h, static_cast<size_t>(b) * p.ldh + h, p.act_bf16);
+    float dh = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) {
+      if (c < C) {
+        const float dl = sLogit[b * kMaxC + c];
+        dw[c] = fmaf(dl, hv, dw[c]);
+        dh = fmaf(dl, wcol[c], dh);
+      }
+    }
+    const float dp = hv > 0.f ? dh : 0.f;
+    dbh += dp;
+    if (h_ok) st_act(p.dpre, static_cast<size_t>(b) * p.ldh + h, p.act_bf16, dp);
+  }
+  // zero the padding rows of dpre so the dW GEMM's batch reduction sees zeros
+  for (int b = B + half; b < p.B_pad; b += 2)
+    if (h_ok) st_act(p.dpre, static_cast<size_t>(b) * p.ldh + h, p.act_bf16, 0.f);
+
+  if (half == 1) {
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) sPart[hh * (kMaxC + 1) + c] = dw[c];
+    sPart[hh * (kMaxC + 1) + kMaxC] = dbh;
+  }
+  __syncthreads();
+  const ResolvedPushH r = resolve_push_h(p.push, seq);
+  const ResolvedPushH rb = resolve_push_h(p.push_bh, seq);
+  if (half == 0 && h_ok) {
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c)
+      if (c < C) push_value(p.push, r.base + p.off_w_last + static_cast<size_t>(c) * H + h,
+                            dw[c] + sPart[hh * (kMaxC + 1) + c]);
+    push_value(p.push_bh, rb.base + p.off_b_hidden + h, dbh + sPart[hh * (kMaxC + 1) + kMaxC]);
+  }
+  if (blockIdx.x == 0 && half == 1 && hh < C) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += sLogit[b * kMaxC + hh];
+    push_value(p.push, r.base + p.off_b_last + hh, s);
+  }
+  if (p.push.mode == PUSH_MAILBOX) {
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      st_release_sys_u32(r.flags + p.item_w_last_base + blockIdx.x, seq);
+      st_release_sys_u32(rb.flags + p.item_b_hidden_base + blockIdx.x, seq);
+      if (blockIdx.x == 0) st_release_sys_u32(r.flags + p.item_b_last, seq);
+    }
+  }
+}
+
+size_t head_smem_bytes(int B_pad, int H, int C) {
+  return sizeof(float) * (static_cast<size_t>(C) * H + static_cast<size_t>(B_pad) * kMaxC + 64 +
+                          static_cast<size_t>(kHeadSlice) * (kMaxC + 1));
+}
+
+cudaError_t launch_head(const HeadParams& p, cudaStream_t stream) {
+  if (p.C > kMaxC || p.B > kMaxB || p.B_pad > kMaxB) return cudaErrorInvalidValue;
+  const size_t smem = head_smem_bytes(p.B_pad, p.H, p.C);
+  cudaError_t e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  const int grid = (p.H + kHeadSlice - 1) / kHeadSlice;
+  head_kernel<<<grid, kHeadThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Stand-alone accuracy reduction (evaluation path): count argmax(logits) == argmax(labels).
+// One warp per row, block partial -> one atomic per block. SURVEY K12.
+// ------------------------------------------------------------------------------------------
+__global__ void accuracy_kernel(const float* __restrict__ logits, const float* __restrict__ labels, int B, int C,
+                                uint32_t* __restrict__ correct) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  uint32_t local = 0;
+  for (int b = warp; b < B; b += nwarps) {
+    float zb = -INFINITY, yb = -INFINITY;
+    int za = 0x7fffffff, ya = 0x7fffffff;
+    for (int c = lane; c < C; c += 32) {
+      const float z = logits[static_cast<size_t>(b) * C + c];
+      const float y = labels[static_cast<size_t>(b) * C + c];
+      if (z > zb) { zb = z; za = c; }
+      if (y > yb) { yb = y; ya = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float zo = __shfl_xor_sync(0xffffffffu, zb, o);
+      const int zao = __shfl_xor_sync(0xffffffffu, za, o);
+      const float yo = __shfl_xor_sync(0xffffffffu, yb, o);
+      const int yao = __shfl_xor_sync(0xffffffffu, ya, o);
+      if (zo > zb || (zo == zb && zao < za)) { zb = zo; za = zao; }
+      if (yo > yb || (yo == yb && yao < ya)) { yb = yo; ya = yao; }
+    }
+    if (lane == 0 && za == ya) ++local;
+  }
+  __shared__ uint32_t s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  if (lane == 0 && local) atomicAdd(&s_cnt, local);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_cnt) atomicAdd(correct, s_cnt);
+}
+
+cudaError_t launch_accuracy(const float* logits, const float* labels, int B, int C, uint32_t* correct,
+                            cudaStream_t stream) {
+  const int threads = 256;
+  int blocks = (B * 32 + threads - 1) / threads;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  accuracy_kernel<<<blocks, threads, 0, stream>>>(logits, labels, B, C, correct);
+  return cudaGetLastError();
+}
+
+}  // namespace dm

@@ -1,0 +1,163 @@
+// Host/device shared structures: kernel parameter blocks and the parameter-server shard layout.
+//
+// Terminology
+//   arena     : one PS shard's flat fp32 parameter buffer (all variables placed on that ps task,
+//               each at an aligned element offset) plus same-shaped Adam m/v buffers and an optional
+//               bf16 shadow copy that workers pull when computing in bf16.
+//   mailbox   : per (worker, slot) gradient staging area living in the *PS's* HBM, same layout as the
+//               arena. Workers write gradient tiles into it with P2P stores from inside their backward
+//               kernels; the PS kernel polls per-item flags and applies.
+//   item      : the unit of push/apply hand-off: a 2-D block {offset, rows, cols, ld} of the arena.
+//               One flag per (worker, slot, item); flag value == push sequence number when ready.
+//   inbox     : tiny buffer in each *worker's* HBM that the PS writes (P2P) so the worker can poll
+//               locally: {acked push seq, global_step}.
+#pragma once
+#include <stdint.h>
+
+namespace dm {
+
+constexpr int kMaxWorkers = 32;
+
+enum PushMode : int {
+  PUSH_LOCAL = 0,    // plain store into a local fp32 gradient buffer (tests, NCCL baseline)
+  PUSH_MAILBOX = 1,  // P2P store into the PS mailbox slot + release flag (Adam / SGD via PS kernel)
+  PUSH_ATOMIC = 2,   // red.add(scale * g) straight into the PS master params (async SGD, no PS kernel)
+};
+
+struct PushTarget {
+  int mode;
+  float scale;              // PUSH_ATOMIC: -lr ; else 1
+  float* base;              // LOCAL: grad arena; MAILBOX: this worker's slot-0 mailbox on the PS; ATOMIC: PS params
+  uint64_t slot_stride;     // elements between mailbox slots
+  uint32_t* flags;          // MAILBOX: this worker's slot-0 flag array on the PS
+  uint32_t flag_slot_stride;
+  uint32_t nslots;
+  const uint32_t* seq_ptr;  // device-local current push sequence number (1-based); null => seq 1 / slot 0
+};
+
+// Epilogue selection for the tcgen05 GEMM  D[M,N] = A[M,K] * B[N,K]^T  (fp32 accumulators in TMEM)
+enum GemmEpilogue : int {
+  // out[n * ldo + m] = f(acc[m][n]) — lanes write consecutive m (coalesced). Forward and dX GEMMs.
+  //   f = (+bias[m]) -> (relu) -> (* (mask[n*ldmask+m] > 0)), optional sums over n (bias grads).
+  EPI_TRANSPOSED = 0,
+  // out[m * ldo + n] = acc[m][n] — each lane owns a row run. dW GEMMs, fused with the gradient push.
+  EPI_ROWMAJOR_PUSH = 1,
+};
+
+struct GemmParams {
+  int M, N, K;          // real extents (tiles are masked against them)
+  int bn;               // N tile, multiple of 16, <= 256
+  int stages;           // smem ring depth
+  int kc_per_split;     // k-chunks handled per blockIdx.z
+  int epi;              // GemmEpilogue
+  int out_bf16;         // EPI_TRANSPOSED: output element type (0 = fp32, 1 = bf16)
+  int relu;
+  int ldo;
+  int ldmask;
+  int mask_bf16;
+  void* out;            // EPI_TRANSPOSED destination
+  const float* bias;    // [M] or null (may be a peer pointer into the PS arena)
+  const void* mask;     // [N][ldmask] activations (relu' = mask > 0) or null
+  PushTarget colsum;    // EPI_TRANSPOSED: optional sum over n of the stored value -> vector[m] (bias grads)
+  uint64_t colsum_offset;  // element offset of the vector inside colsum.base
+  int colsum_item_base; // flag item index of mtile 0 of the vector
+  int has_colsum;
+  PushTarget push;      // EPI_ROWMAJOR_PUSH destination
+  uint64_t push_offset; // element offset of the variable inside push.base
+  int push_item_base;   // first flag item index for this variable's tiles (tile = mtile * ntiles + ntile)
+  int pad_;
+  uint32_t* bump_seq;   // if set, CTA (0,0,0) increments it: the first kernel of a step opens a new push seq
+};
+
+// Softmax-cross-entropy head (last dense layer + loss + its gradients), see head_sm100.cu
+enum LossKind : int {
+  LOSS_BOOK = 0,  // -mean over B x C of labels * log(clip(softmax, 1e-10, 1))   (reference DS:52-53)
+  LOSS_XENT = 1,  // mean over B of softmax_cross_entropy_with_logits               (reference DS:35)
+};
+
+struct StepResult {  // written once per worker step, read back by the host (D2H)
+  float loss;
+  uint32_t global_step;
+  uint32_t correct;   // argmax(logits) == argmax(labels) count over the batch (accuracy numerator)
+  uint32_t seq;       // push sequence number of this step
+};
+
+struct HeadParams {
+  int B;            // real batch
+  int B_pad;        // rows allocated in h / dpre (multiple of 16)
+  int H;            // last hidden width
+  int C;            // classes
+  int loss_kind;
+  int act_bf16;     // h / dpre element type
+  int ldh;
+  int compute_grads;  // 0 = eval only (loss + accuracy)
+  const void* h;        // [B_pad][ldh]
+  const float* labels;  // [B_pad][C] one-hot (or soft) labels
+  const float* w_last;  // [C][H] fp32 master on the PS (peer pointer)
+  const float* b_last;  // [C]
+  void* dpre;           // [B_pad][ldh] gradient wrt last hidden pre-activation (relu' applied)
+  PushTarget push;      // all three small gradients go to the same PS shard set as their variables:
+  PushTarget push_bh;   //   (w_last, b_last use `push`; the hidden bias may live on another shard)
+  uint64_t off_w_last, off_b_last, off_b_hidden;
+  int item_w_last_base; // + blockIdx.x
+  int item_b_last;
+  int item_b_hidden_base;  // + blockIdx.x
+  int pad_;
+  StepResult* result;      // device buffer (copied D2H by the step graph)
+  // PS bookkeeping
+  uint32_t* seq_ptr;         // local; bumped by the first kernel of the step (GemmParams::bump_seq), read here
+  const uint32_t* inbox;     // local [n_inbox][2] = {ack_seq, global_step} per PS shard, written by the PS; or null
+  uint32_t* ps_global_step;  // peer pointer (atomic mode: atom.add; local mode: null)
+  uint32_t nslots;
+  uint32_t n_inbox;          // number of PS shards this worker pushes to
+};
+
+// One unit of PS apply work.
+struct PsItem {
+  uint64_t offset;  // element offset inside the arena
+  int rows, cols;
+  int ld;
+  int flags;        // bit0: refresh bf16 shadow for this block
+};
+
+struct PsItemState {  // persisted across serve-kernel launches and checkpointed
+  uint32_t t;        // number of pushes applied to this item (Adam step count)
+  float beta1_pow;
+  float beta2_pow;
+  uint32_t pad_;
+};
+
+enum OptimizerKind : int { OPT_SGD = 0, OPT_ADAM = 1 };
+enum ApplyMode : int {
+  APPLY_PER_PUSH = 0,  // reference semantics: every worker push is its own optimizer step
+  APPLY_MERGED = 1,    // pushes that are ready at the same poll are summed and applied as one step
+};
+
+struct PsServeParams {
+  float* params;
+  float* adam_m;
+  float* adam_v;
+  uint16_t* shadow_bf16;       // null if unused
+  const PsItem* items;
+  PsItemState* item_state;
+  int n_items;
+  int n_workers;
+  int nslots;
+  int opt;
+  int apply_mode;
+  float lr, beta1, beta2, eps;
+  const float* mailbox;        // [n_workers][nslots][arena_elems]
+  uint64_t arena_elems;
+  uint32_t* flags;             // [n_workers][nslots][n_items]
+  uint32_t* next_seq;          // [n_workers][n_items] next expected push seq (persisted)
+  uint32_t* consumed;          // [n_workers][nslots] items consumed of the in-flight push
+  uint32_t* global_step;       // shard-local step counter (only shard 0's is authoritative)
+  uint32_t* worker_done;       // [n_workers] set remotely by workers when they leave the session
+  volatile uint32_t* host_stop;  // host-mapped stop request
+  // Table (in the PS's own memory) of peer pointers to each worker's inbox {ack_seq, global_step}; the host
+  // patches entries while the kernel runs when a worker attaches late, so it is read with volatile loads.
+  uint32_t* volatile* inbox_table;
+  uint32_t* exit_counter;      // CTAs increment on exit (debug / clean shutdown)
+};
+
+}  // namespace dm
