@@ -1,0 +1,292 @@
+"""Headline benchmark: MNIST-MLP steps/sec of the parameter-server engine, whole box, device-timed.
+
+    python bench.py --gpus 1 --steps 2000 --warmup 50
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Topology (BASELINE.json configs): N = 1 -> 1 ps + 1 worker sharing the GPU (one process);
+N >= 2 -> rank 0 is the dedicated ps GPU, ranks 1..N-1 are workers (N = 8 -> "1 ps + 7 workers").
+Model/config: the reference's live model (784-100-10 "book" MLP, batch 32 per worker, Adam lr 1e-4,
+asynchronous per-push apply on the ps) with synthetic 28x28 data and random-init weights.
+
+Two numbers are reported (see the JSON keys):
+  value : K steps per worker, inputs streamed from a device-resident 55 000-image dataset (172 MB > L2),
+          timed with CUDA events on the worker's compute stream; the timed region ends with a stream-ordered
+          wait for the PS acknowledgement of the last push, so optimizer applies are inside it.
+  e2e   : the same K steps through the public API (`Worker.run_steps`): native next_batch gather into pinned
+          memory, H2D copy of every batch, step graph, 16-byte result D2H per step; wall clock between
+          device synchronisations.
+Both take the max over ranks; throughput = (workers x K) / max elapsed.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import torch
+
+REFERENCE_UNAVAILABLE = (
+    "reference needs TensorFlow 1.x (tf.contrib, tf.app.flags, tf.train.Server); no tensorflow wheel in "
+    "/opt/wheelhouse, none for Python 3.12, no network; /root/reference has no setup.py/pyproject so "
+    "`pip install --target baseline/_ref /root/reference` fails with 'not installable'"
+)
+
+
+def parse_args(argv=None):
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=2000)
+    p.add_argument("--warmup", type=int, default=50)
+    p.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    p.add_argument("--model", default="book")
+    p.add_argument("--hidden_units", type=int, default=100)
+    p.add_argument("--batch_size", type=int, default=32)
+    p.add_argument("--optimizer", choices=["adam", "sgd"], default="adam")
+    p.add_argument("--learning_rate", type=float, default=1e-4)
+    p.add_argument("--dtype", choices=["fp32", "bf16"], default="fp32")
+    p.add_argument("--push_mode", choices=["mailbox", "atomic"], default="mailbox")
+    p.add_argument("--apply_mode", choices=["per_push", "merged"], default="per_push")
+    p.add_argument("--num_ps", type=int, default=1)
+    p.add_argument("--sharding", choices=["round_robin", "byte_balanced"], default="round_robin")
+    p.add_argument("--nslots", type=int, default=2)
+    p.add_argument("--skip_e2e", action="store_true")
+    return p.parse_args(argv)
+
+
+def main(argv=None) -> int:
+    args = parse_args(argv)
+    if args.impl == "reference":
+        print(json.dumps({"impl": "reference", "unavailable": REFERENCE_UNAVAILABLE}))
+        return 0
+
+    import torch.distributed as dist
+
+    from dist_mnist_b200 import _native as N
+    from dist_mnist_b200.cluster import ClusterSpec, Rendezvous
+    from dist_mnist_b200.models import mlp
+    from dist_mnist_b200.parallel.config import EngineConfig, OptimizerConfig
+    from dist_mnist_b200.parallel.ps import ParameterServer
+    from dist_mnist_b200.parallel.worker import Worker
+    from dist_mnist_b200.session import InProcessCluster
+    from dist_mnist_b200.utils import data as data_utils
+    from dist_mnist_b200.utils.metrics import ClockSampler, StreamTimer
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "bench.py needs a CUDA device (B200); none visible"}))
+        return 1
+    N.lib()  # fail loudly if the native library is missing: there is no eager fallback for the hot path
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = args.gpus
+    if world > 1 and world != n_gpus:
+        raise SystemExit(f"--gpus {n_gpus} but WORLD_SIZE={world}")
+    if world == 1 and n_gpus != 1:
+        raise SystemExit("for --gpus N > 1 launch with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    spec = mlp.get_model(args.model, args.hidden_units)
+    opt = OptimizerConfig(args.optimizer, args.learning_rate)
+    cfg = EngineConfig(backend="cuda", dtype=args.dtype, nslots=args.nslots, apply_mode=args.apply_mode,
+                       push_mode=args.push_mode, sharding=args.sharding)
+    cfg.validate(opt)
+    K, W, B = args.steps, args.warmup, args.batch_size
+
+    # ---------------- data (allocated before any persistent PS kernel exists on this GPU) ----------------
+    ds = data_utils.synthetic_mnist(data_utils.TRAIN_SIZE, seed=0)
+    is_worker_rank = world == 1 or rank >= args.num_ps
+    dev_x = dev_y = None
+    pin_x = pin_y = None
+    if is_worker_rank:
+        dev = torch.device("cuda", local_rank)
+        tdtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
+        dev_x = ds.images.to(tdtype).to(dev).contiguous()      # 55000 x 784: 172 MB fp32 (> 126 MB L2)
+        dev_y = ds.labels.to(dev).contiguous()
+        torch.cuda.synchronize()
+
+    # ---------------- bring-up ----------------
+    ps_list, worker, inproc = [], None, None
+    loaders = {}
+
+    def make_loader(w):
+        loaders["l"] = w.make_loader(ds.images, ds.labels, seed=rank)
+
+    if world == 1:
+        inproc = InProcessCluster(spec, opt, cfg, batch_size=B, num_ps=args.num_ps, device=local_rank, seed=0,
+                                  setup_hook=make_loader)
+        ps_list, worker = inproc.ps, inproc.worker
+        n_workers = 1
+    else:
+        num_ps = args.num_ps
+        n_workers = world - num_ps
+        if n_workers < 1:
+            raise SystemExit("need at least one worker rank")
+        addr = os.environ.get("MASTER_ADDR", "127.0.0.1")
+        port = int(os.environ.get("MASTER_PORT", "29500"))
+        cluster = ClusterSpec(tuple(f"{addr}:{port + 23 + k}" for k in range(num_ps)),
+                              tuple(f"{addr}:{port + 200 + i}" for i in range(n_workers)))
+        if rank < num_ps:
+            rdv = Rendezvous(cluster, "ps", rank)
+            ps = ParameterServer(cluster, rank, spec, opt, cfg, device=local_rank, rdv=rdv)
+            ps.start()
+            ps_list = [ps]
+        else:
+            w = rank - num_ps
+            rdv = Rendezvous(cluster, "worker", w)
+            worker = Worker(cluster, w, spec, opt, cfg, batch_size=B, device=local_rank, rdv=rdv)
+            worker.connect()
+            make_loader(worker)
+            if worker.is_chief:
+                worker.initialize_variables(seed=0)
+            worker.wait_ready()
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+
+    def full_sync():
+        """barrier + torch.cuda.synchronize() on every rank. A running persistent PS kernel would make the device
+        synchronise hang, so ps tasks stop their serve kernel (state stays in HBM), synchronise, and relaunch it."""
+        if worker is not None:
+            worker.wait_applied()
+        barrier()
+        for ps in ps_list:
+            ps.stop()
+        torch.cuda.synchronize()
+        for ps in ps_list:
+            ps.restart()
+        barrier()
+
+    elapsed_ms = 0.0
+    e2e_s = 0.0
+    h2d_bytes = d2h_bytes = 0
+    if worker is not None:
+        assert worker.ld_in == dev_x.shape[1]
+        n_rows = dev_x.shape[0] - worker.B_pad
+        xrow, yrow = dev_x.shape[1] * dev_x.element_size(), dev_y.shape[1] * 4
+
+        def resident_steps(n, start):
+            for i in range(n):
+                r = ((start + i) * B) % n_rows
+                worker.submit_resident(dev_x.data_ptr() + r * xrow, dev_y.data_ptr() + r * yrow)
+
+        resident_steps(max(W, 3), 0)
+        loader = loaders["l"]
+
+    sampler = ClockSampler(interval_ms=100, gpu_indices=list(range(n_gpus))) if rank == 0 else None
+    full_sync()
+    if sampler:
+        sampler.start()
+
+    # ---------------- timed region 1: device-timed steps ----------------
+    launches_before = worker.kernel_launches() if worker is not None else 0
+    if worker is not None:
+        timer = StreamTimer(worker.compute_stream, local_rank)
+        timer.start()
+        resident_steps(K, max(W, 3))
+        worker.enqueue_wait_ack()
+        timer.stop()
+        elapsed_ms = timer.elapsed_ms()
+    full_sync()
+    launches = (worker.kernel_launches() - launches_before + 1) if worker is not None else 0
+
+    # ---------------- timed region 2: end to end through the public API ----------------
+    if not args.skip_e2e:
+        if worker is not None:
+            worker.run_steps(max(W, 3), loader)
+        full_sync()
+        if worker is not None:
+            t0 = time.perf_counter()
+            outs = worker.run_steps(K, loader)
+            worker.wait_applied()
+            torch.cuda.synchronize()
+            e2e_s = time.perf_counter() - t0
+            assert len(outs) == K
+            h2d_bytes = worker.x_bytes + worker.y_bytes
+            d2h_bytes = C.sizeof(N.StepResult)
+        full_sync()
+    clocks = sampler.stop() if sampler else None
+
+    # ---------------- reduce over ranks ----------------
+    final_step = worker.read_global_step() if (worker is not None and worker.is_chief) else 0
+    kps = worker.kernels_per_step if worker is not None else 0
+    stats = torch.tensor([elapsed_ms, e2e_s, float(launches), float(h2d_bytes), float(d2h_bytes), float(final_step),
+                          float(kps)], dtype=torch.float64, device="cuda")
+    mx = stats.clone()
+    sm = stats.clone()
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+
+    if rank == 0:
+        max_ms, max_e2e = float(mx[0]), float(mx[1])
+        value = n_workers * K / (max_ms / 1e3)
+        n_params = spec.num_params
+        out = {
+            "metric": "MNIST-MLP steps/sec (whole box, device-timed, max over ranks)",
+            "value": value,
+            "unit": "steps/s",
+            "n_gpus": n_gpus,
+            "steps": K,
+            "warmup": max(W, 3),
+            "ms_per_step": max_ms / K,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": ("fp32 storage, tf32 tensor-core multiply, fp32 accumulate" if args.dtype == "fp32" else "bf16"),
+            "data": "synthetic",
+            "config": {
+                "model": f"784-{'-'.join(str(h) for h in spec.hidden)}-10 MLP ({spec.name}), {n_params} params",
+                "global_batch": B * n_workers,
+                "per_worker_batch": B,
+                "seq_len": None,
+                "parallelism": (f"{args.num_ps}ps+{n_workers}worker async parameter server"
+                                + (" (ps and worker share the GPU)" if world == 1 else " (dedicated ps GPU)")),
+                "optimizer": f"{args.optimizer} lr={args.learning_rate}",
+                "apply": f"{args.push_mode}/{args.apply_mode}",
+                "l2_policy": "inputs stream from a 55000x784 device-resident dataset (172 MB fp32 > 126 MB L2); "
+                             "parameters (0.3 MB) stay L2-resident as in real training",
+                "global_step_after_run": int(mx[5]),
+            },
+            "clocks": clocks,
+            "gpu_launches": int(sm[2]),
+            "kernels_per_step": int(mx[6]),
+            "impl": "ours",
+        }
+        if not args.skip_e2e:
+            out["e2e"] = {
+                "value": n_workers * K / max_e2e,
+                "unit": "steps/s",
+                "ms_per_step": max_e2e * 1e3 / K,
+                "h2d_bytes_per_step": int(mx[3]),
+                "d2h_bytes_per_step": int(mx[4]),
+                "timing": "wall clock between device synchronisations, max over ranks",
+            }
+        print(json.dumps(out), flush=True)
+
+    # ---------------- teardown ----------------
+    if inproc is not None:
+        inproc.close()
+    else:
+        if worker is not None:
+            worker.finish()
+        barrier()
+        for ps in ps_list:
+            ps.stop()
+        if worker is not None:
+            worker.close()
+        for ps in ps_list:
+            ps.close()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

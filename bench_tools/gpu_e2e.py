@@ -1,0 +1,151 @@
+"""Single-GPU end-to-end checks of the engine (ps + worker in one process on cuda:0).
+
+    python -m bench_tools.gpu_e2e traj        # lock-step trajectory vs a plain PyTorch fp32 re-implementation
+    python -m bench_tools.gpu_e2e throughput  # pipelined native loop, steps/s
+    python -m bench_tools.gpu_e2e all
+"""
+from __future__ import annotations
+
+import subprocess
+import sys
+import time
+import traceback
+
+import torch
+
+from dist_mnist_b200.models import mlp
+from dist_mnist_b200.parallel.config import EngineConfig, OptimizerConfig
+from dist_mnist_b200.session import InProcessCluster
+from dist_mnist_b200.utils import data
+
+
+def ref_step(spec, params, m, v, t, x, y, opt):
+    loss, grads, _ = mlp.manual_loss_and_grads(spec, params, x, y)
+    t += 1
+    for k in params:
+        g = grads[k]
+        if opt.kind == "sgd":
+            params[k] = params[k] - opt.lr * g
+        else:
+            m[k] = opt.beta1 * m[k] + (1 - opt.beta1) * g
+            v[k] = opt.beta2 * v[k] + (1 - opt.beta2) * g * g
+            lr_t = opt.lr * (1 - opt.beta2 ** t) ** 0.5 / (1 - opt.beta1 ** t)
+            params[k] = params[k] - lr_t * m[k] / (v[k].sqrt() + opt.eps)
+    return float(loss), t
+
+
+def wait_gstep(worker, target, timeout=10.0):
+    t0 = time.time()
+    while worker.read_global_step() < target:
+        if time.time() - t0 > timeout:
+            raise TimeoutError(f"global_step stuck at {worker.read_global_step()} < {target}")
+        time.sleep(0.0005)
+
+
+def check_traj() -> bool:
+    ok = True
+    ds = data.synthetic_mnist(4096, seed=3)
+    cases = [
+        ("book", "adam", "fp32", "mailbox", 1, 32, 5e-2),
+        ("book", "sgd", "fp32", "mailbox", 1, 32, 5e-2),
+        ("book", "sgd", "fp32", "atomic", 1, 32, 5e-2),
+        ("book", "adam", "fp32", "mailbox", 2, 32, 5e-2),
+        ("zhihu", "adam", "fp32", "mailbox", 2, 100, 5e-2),
+        ("wide", "adam", "bf16", "mailbox", 2, 64, 2e-1),
+        ("book", "adam", "bf16", "mailbox", 1, 32, 2e-1),
+    ]
+    for (model, okind, dtype, push, nps, batch, tol) in cases:
+        name = f"traj model={model} opt={okind} dtype={dtype} push={push} ps={nps} B={batch}"
+        try:
+            spec = mlp.get_model(model)
+            lr = 1e-3 if okind == "adam" else 5e-2
+            opt = OptimizerConfig(okind, lr)
+            cfg = EngineConfig(backend="cuda", dtype=dtype, push_mode=push, sharding="round_robin")
+            params = mlp.init_params(spec, seed=7)
+            ref_p = {k: t.clone() for k, t in params.items()}
+            ref_m = {k: torch.zeros_like(t) for k, t in params.items()}
+            ref_v = {k: torch.zeros_like(t) for k, t in params.items()}
+            t = 0
+            it = data.BatchIterator(ds, seed=1)
+            with InProcessCluster(spec, opt, cfg, batch_size=batch, num_ps=nps, params=params) as cl:
+                w = cl.worker
+                worst = 0.0
+                n_steps = 12
+                for i in range(n_steps):
+                    x, y = it.next_batch(batch)
+                    r = w.step(x, y)
+                    wait_gstep(w, i + 1)
+                    lref, t = ref_step(spec, ref_p, ref_m, ref_v, t, x, y, opt)
+                    worst = max(worst, abs(r.loss - lref) / (abs(lref) + 1e-9))
+                got = w.read_variables()
+                perr = max(float((got[k] - ref_p[k]).norm() / (ref_p[k].norm() + 1e-9)) for k in got)
+                gs = w.read_global_step()
+                acc_loss, acc = w.evaluate(ds.images[:512], ds.labels[:512])
+            good = worst < tol and perr < tol and gs == n_steps
+            print(f"[{'PASS' if good else 'FAIL'}] {name}: worst_loss_rel={worst:.2e} param_rel={perr:.2e} "
+                  f"global_step={gs} eval_loss={acc_loss:.4f} acc={acc:.3f}", flush=True)
+            ok &= good
+        except Exception:
+            traceback.print_exc()
+            print(f"[FAIL] {name}: exception", flush=True)
+            ok = False
+    return ok
+
+
+def check_throughput() -> bool:
+    ok = True
+    ds = data.synthetic_mnist(data.TRAIN_SIZE, seed=0)
+    for (model, okind, dtype, push, batch) in [("book", "adam", "fp32", "mailbox", 32),
+                                                ("book", "sgd", "fp32", "atomic", 32),
+                                                ("book", "sgd", "fp32", "mailbox", 32),
+                                                ("wide", "adam", "bf16", "mailbox", 32)]:
+        name = f"throughput model={model} opt={okind} dtype={dtype} push={push} B={batch}"
+        try:
+            spec = mlp.get_model(model)
+            opt = OptimizerConfig(okind, 1e-4 if okind == "adam" else 1e-2)
+            cfg = EngineConfig(backend="cuda", dtype=dtype, push_mode=push)
+            with InProcessCluster(spec, opt, cfg, batch_size=batch) as cl:
+                w = cl.worker
+                loader = w.make_loader(ds.images, ds.labels, seed=0)
+                outs = w.run_steps(200, loader)  # warm-up
+                first_loss = outs[0].loss
+                torch.cuda.synchronize() if False else None
+                t0 = time.perf_counter()
+                n = 4000
+                outs = w.run_steps(n, loader)
+                dt = time.perf_counter() - t0
+                w.drain()
+                time.sleep(0.05)
+                gs = w.read_global_step()
+                print(f"[PASS] {name}: {n / dt:.0f} steps/s e2e (wall), {dt / n * 1e6:.1f} us/step, loss {first_loss:.4f} -> "
+                      f"{outs[-1].loss:.4f}, global_step={gs} (expected {n + 200}), kernels/step={w.kernels_per_step}",
+                      flush=True)
+                ok &= gs == n + 200
+        except Exception:
+            traceback.print_exc()
+            print(f"[FAIL] {name}: exception", flush=True)
+            ok = False
+    return ok
+
+
+CHECKS = {"traj": check_traj, "throughput": check_throughput}
+
+
+def main(argv) -> int:
+    which = argv[0] if argv else "all"
+    if which == "all":
+        rc = 0
+        for g in CHECKS:
+            print(f"===== {g} =====", flush=True)
+            try:
+                code = subprocess.run([sys.executable, "-m", "bench_tools.gpu_e2e", g], timeout=400).returncode
+            except subprocess.TimeoutExpired:
+                code = 124
+            print(f"===== {g}: exit {code} =====", flush=True)
+            rc |= int(code != 0)
+        return rc
+    return 0 if CHECKS[which]() else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main(sys.argv[1:]))

@@ -63,6 +63,42 @@ def _run(cmd: list[str], verbose: bool) -> None:
         print(res.stdout, res.stderr, flush=True)
 
 
+HASH_PATH = PKG_DIR / (LIB_NAME + ".srchash")
+
+
+def source_hash() -> str:
+    """Content hash of every source, header and the build recipe (mtimes do not survive repo snapshots)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for name in sorted(CUDA_SOURCES + CXX_SOURCES + HEADERS):
+        h.update(name.encode())
+        h.update((CSRC / name).read_bytes())
+    h.update(" ".join(NVCC_FLAGS + CXX_FLAGS).encode())
+    return h.hexdigest()
+
+
+def is_current() -> bool:
+    return LIB_PATH.exists() and HASH_PATH.exists() and HASH_PATH.read_text().strip() == source_hash()
+
+
+def build_if_stale(verbose: bool = False) -> Path:
+    """Rebuild only when the sources changed since the shared object was produced (cross-process safe)."""
+    if is_current():
+        return LIB_PATH
+    import fcntl
+
+    BUILD_DIR.mkdir(parents=True, exist_ok=True)
+    with open(BUILD_DIR / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not is_current():
+                build(force=True, verbose=verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+    return LIB_PATH
+
+
 def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> Path:
     """Compile (if stale) and return the path of the shared object."""
     cuda = _cuda_home()
@@ -95,6 +131,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
             verbose,
         )
         os.replace(tmp, LIB_PATH)
+    HASH_PATH.write_text(source_hash() + "\n")
     return LIB_PATH
 
 

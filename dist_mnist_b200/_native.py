@@ -68,7 +68,7 @@ class HeadParams(C.Structure):
         ("loss_kind", C.c_int), ("act_bf16", C.c_int), ("ldh", C.c_int), ("compute_grads", C.c_int),
         ("h", C.c_void_p), ("labels", C.c_void_p), ("w_last", C.c_void_p), ("b_last", C.c_void_p),
         ("dpre", C.c_void_p),
-        ("push", PushTarget), ("push_bh", PushTarget),
+        ("push", PushTarget), ("push_bl", PushTarget), ("push_bh", PushTarget),
         ("off_w_last", C.c_uint64), ("off_b_last", C.c_uint64), ("off_b_hidden", C.c_uint64),
         ("item_w_last_base", C.c_int), ("item_b_last", C.c_int), ("item_b_hidden_base", C.c_int), ("pad_", C.c_int),
         ("result", C.c_void_p),
@@ -152,6 +152,7 @@ def _declare(l: C.CDLL) -> None:
         "dm_launch_dense_apply": (i, [vp, vp, vp, vp, vp, sz, i, f, f, f, f, u32, vp]),
         "dm_launch_shadow_refresh": (i, [vp, vp, sz, vp]),
         "dm_launch_worker_done": (i, [vp, vp, vp]),
+        "dm_launch_wait_ack": (i, [vp, u32, vp, vp]),
         "dm_launch_p2p_copy": (i, [vp, vp, sz, i, i, vp, u32, vp]),
         "dm_launch_p2p_reduce_apply": (i, [vp, vp, i, sz, f, i, vp]),
         "dm_launch_pingpong": (i, [vp, vp, i, i, vp, vp]),
@@ -167,6 +168,8 @@ def _declare(l: C.CDLL) -> None:
         "dm_cpu_ps_running": (i, [vp]),
         "dm_cpu_ps_applied": (u64, [vp]),
         "dm_cpu_ps_join": (i, [vp]),
+        "dm_prepare_kernels": (i, [i]),
+        "dm_exec_acquire_slot": (i, [vp, C.POINTER(i)]),
         "dm_exec_last_error": (C.c_char_p, []),
         "dm_loader_create": (vp, [vp, vp, sz, sz, sz, sz, sz, i, u64, i]),
         "dm_loader_next": (None, [vp, vp, vp]),
@@ -199,13 +202,17 @@ def lib(build_if_missing: bool = True) -> C.CDLL:
     if _lib is not None:
         return _lib
     path = lib_path()
-    if not path.exists() or os.environ.get("DM_REBUILD") == "1":
-        if not build_if_missing:
+    if os.environ.get("DM_NO_BUILD") != "1":
+        if not build_if_missing and not path.exists():
             raise NativeError(f"native library {path} is missing; run `python -m dist_mnist_b200._build`")
         try:
-            _build.build(force=os.environ.get("DM_REBUILD") == "1")
+            if os.environ.get("DM_REBUILD") == "1":
+                _build.build(force=True)
+            else:
+                _build.build_if_stale()   # content-hash check; no-op when the in-tree .so matches the sources
         except Exception as e:  # pragma: no cover - toolchain problems
-            raise NativeError(f"building {path} failed: {e}") from e
+            if not path.exists():
+                raise NativeError(f"building {path} failed: {e}") from e
     try:
         l = C.CDLL(str(path))
     except OSError as e:
@@ -241,6 +248,18 @@ def check(rc: int, what: str = "") -> None:
 
 def current_stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+_prepared_devices = set()
+
+
+def ensure_prepared(device: int | None = None) -> None:
+    """Opt the big-shared-memory kernels in (cudaFuncSetAttribute) once per device, outside graph capture."""
+    if device is None:
+        device = torch.cuda.current_device()
+    if device not in _prepared_devices:
+        check(lib().dm_prepare_kernels(device), "prepare kernels")
+        _prepared_devices.add(device)
 
 
 def make_tensor_map(ptr: int, dtype: int, dim0: int, dim1: int, stride1_bytes: int, box0: int, box1: int,

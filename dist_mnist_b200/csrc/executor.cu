@@ -199,6 +199,16 @@ int dm_exec_end_capture(void* h, int slot, int kernels_in_graph) {
   return 0;
 }
 
+// Retire (wait for) the step that last used the next slot and return that slot's index: after this call the
+// slot's pinned staging buffers may be overwritten with the next batch.
+int dm_exec_acquire_slot(void* h, int* slot) {
+  Executor* ex = static_cast<Executor*>(h);
+  const int idx = static_cast<int>(ex->submitted % ex->slots.size());
+  if (ex->retire(ex->slots[idx]) != 0) return -1;
+  *slot = idx;
+  return 0;
+}
+
 // Submit one step. x_src / y_src: host (pinned) or device pointers of x_bytes / y_bytes, or null to reuse the
 // data already resident in the slot's device buffers. Returns the 1-based ticket.
 int dm_exec_submit(void* h, const void* x_src, const void* y_src, uint64_t* ticket) {

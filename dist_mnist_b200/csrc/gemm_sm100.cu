@@ -270,13 +270,35 @@ size_t gemm_smem_bytes(int bn, int stages) {
   return static_cast<size_t>(stages) * (kABytes + bn * 128) + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
 }
 
+constexpr int kMaxDynSmem = 227 * 1024;
+
+template <typename T, bool A_MN, bool B_MN>
+static cudaError_t prepare_one() {
+  return cudaFuncSetAttribute(gemm_tcgen05_kernel<T, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              kMaxDynSmem);
+}
+
+// Opt every instantiation into the full 227 KB of dynamic shared memory once per device, outside of any
+// stream capture (launches themselves then carry no attribute calls and are graph-capturable).
+cudaError_t prepare_gemm_kernels() {
+  cudaError_t e;
+#define DM_PREP(T)                                              \
+  if ((e = prepare_one<T, false, false>()) != cudaSuccess) return e; \
+  if ((e = prepare_one<T, true, true>()) != cudaSuccess) return e;   \
+  if ((e = prepare_one<T, true, false>()) != cudaSuccess) return e;  \
+  if ((e = prepare_one<T, false, true>()) != cudaSuccess) return e;
+  DM_PREP(float)
+  DM_PREP(__nv_bfloat16)
+#undef DM_PREP
+  return cudaSuccess;
+}
+
 template <typename T, bool A_MN, bool B_MN>
 static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, dim3 grid,
                               cudaStream_t stream) {
   auto kern = gemm_tcgen05_kernel<T, A_MN, B_MN>;
   const size_t smem = gemm_smem_bytes(p.bn, p.stages);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (e != cudaSuccess) return e;
+  if (smem > static_cast<size_t>(kMaxDynSmem)) return cudaErrorInvalidValue;
   kern<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p);
   return cudaGetLastError();
 }

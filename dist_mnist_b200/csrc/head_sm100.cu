@@ -91,7 +91,12 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
           }
         }
       }
-      gstep = inbox[1];  // shard 0 owns global_step (reference: first variable created, DS:91)
+      // entry 0 belongs to the shard that owns global_step (first variable created, reference DS:91).
+      // global_step as of our last acknowledged push + our own pushes since then: exact with one worker,
+      // a lower bound under concurrency (the reference's fetched value is equally unordered w.r.t. peers).
+      const uint32_t ack = inbox[0];
+      __threadfence();
+      gstep = inbox[1] + (seq - ack);
     }
     s_gstep = gstep;
   }
@@ -236,6 +241,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
   __syncthreads();
   const ResolvedPushH r = resolve_push_h(p.push, seq);
   const ResolvedPushH rb = resolve_push_h(p.push_bh, seq);
+  const ResolvedPushH rl = resolve_push_h(p.push_bl, seq);
   if (half == 0 && h_ok) {
 #pragma unroll
     for (int c = 0; c < kMaxC; ++c)
@@ -246,7 +252,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
   if (blockIdx.x == 0 && half == 1 && hh < C) {
     float s = 0.f;
     for (int b = 0; b < B; ++b) s += sLogit[b * kMaxC + hh];
-    push_value(p.push, r.base + p.off_b_last + hh, s);
+    push_value(p.push_bl, rl.base + p.off_b_last + hh, s);
   }
   if (p.push.mode == PUSH_MAILBOX) {
     __threadfence_system();
@@ -254,7 +260,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
     if (tid == 0) {
       st_release_sys_u32(r.flags + p.item_w_last_base + blockIdx.x, seq);
       st_release_sys_u32(rb.flags + p.item_b_hidden_base + blockIdx.x, seq);
-      if (blockIdx.x == 0) st_release_sys_u32(r.flags + p.item_b_last, seq);
+      if (blockIdx.x == 0) st_release_sys_u32(rl.flags + p.item_b_last, seq);
     }
   }
 }
@@ -264,12 +270,16 @@ size_t head_smem_bytes(int B_pad, int H, int C) {
                           static_cast<size_t>(kHeadSlice) * (kMaxC + 1));
 }
 
+constexpr int kHeadMaxSmem = 200 * 1024;
+
+cudaError_t prepare_head_kernel() {
+  return cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadMaxSmem);
+}
+
 cudaError_t launch_head(const HeadParams& p, cudaStream_t stream) {
   if (p.C > kMaxC || p.B > kMaxB || p.B_pad > kMaxB) return cudaErrorInvalidValue;
   const size_t smem = head_smem_bytes(p.B_pad, p.H, p.C);
-  cudaError_t e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
-  if (e != cudaSuccess) return e;
+  if (smem > static_cast<size_t>(kHeadMaxSmem)) return cudaErrorInvalidValue;
   const int grid = (p.H + kHeadSlice - 1) / kHeadSlice;
   head_kernel<<<grid, kHeadThreads, smem, stream>>>(p);
   return cudaGetLastError();

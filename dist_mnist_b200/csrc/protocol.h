@@ -96,8 +96,9 @@ struct HeadParams {
   const float* w_last;  // [C][H] fp32 master on the PS (peer pointer)
   const float* b_last;  // [C]
   void* dpre;           // [B_pad][ldh] gradient wrt last hidden pre-activation (relu' applied)
-  PushTarget push;      // all three small gradients go to the same PS shard set as their variables:
-  PushTarget push_bh;   //   (w_last, b_last use `push`; the hidden bias may live on another shard)
+  PushTarget push;      // dW_last   — each small gradient goes to the shard that owns its variable
+  PushTarget push_bl;   // db_last     (round-robin placement puts sm_w and sm_b on different ps tasks)
+  PushTarget push_bh;   // db of the last hidden layer
   uint64_t off_w_last, off_b_last, off_b_hidden;
   int item_w_last_base; // + blockIdx.x
   int item_b_last;

@@ -282,6 +282,26 @@ cudaError_t launch_shadow_refresh(const float* src, uint16_t* dst, size_t n, cud
   return cudaGetLastError();
 }
 
+// Stream-ordered "all my pushes are applied" fence on the worker: spins (locally — the PS writes the inbox
+// into the worker's HBM) until every shard has acknowledged the worker's latest push. Lets a CUDA-event
+// timed region include the PS-side apply of its last step.
+__global__ void wait_ack_kernel(const uint32_t* inbox, uint32_t n_inbox, const uint32_t* seq_ptr) {
+  const uint32_t seq = *reinterpret_cast<const volatile uint32_t*>(seq_ptr);
+  const uint64_t t0 = globaltimer_ns();
+  for (uint32_t i = 0; i < n_inbox; ++i) {
+    while (static_cast<int32_t>(ld_acquire_sys_u32(inbox + 2 * i) - seq) < 0) {
+      if (globaltimer_ns() - t0 > DM_SPIN_TIMEOUT_NS) {
+        printf("[dm] wait_ack: shard %u stuck at ack=%u, seq=%u\n", i, inbox[2 * i], seq);
+        __trap();
+      }
+    }
+  }
+}
+cudaError_t launch_wait_ack(const uint32_t* inbox, uint32_t n_inbox, const uint32_t* seq_ptr, cudaStream_t stream) {
+  wait_ack_kernel<<<1, 1, 0, stream>>>(inbox, n_inbox, seq_ptr);
+  return cudaGetLastError();
+}
+
 // Worker leaves the session: publish last_seq + 1 into the PS's worker_done slot (peer store).
 __global__ void worker_done_kernel(uint32_t* done_slot, const uint32_t* seq_ptr) {
   __threadfence_system();

@@ -74,6 +74,7 @@ class GemmPlan:
 
     def launch(self, stream: Optional[int] = None) -> None:
         s = N.current_stream_ptr() if stream is None else stream
+        N.ensure_prepared()
         N.check(
             N.lib().dm_launch_gemm(
                 C.addressof(self.tm_a), C.addressof(self.tm_b), C.addressof(self.params), self.dtype,

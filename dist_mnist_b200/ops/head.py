@@ -27,12 +27,14 @@ class HeadPlan:
 
     def launch(self, stream: Optional[int] = None) -> None:
         s = N.current_stream_ptr() if stream is None else stream
+        N.ensure_prepared()
         N.check(N.lib().dm_launch_head(C.addressof(self.params), s), f"launch {self.name}")
 
 
 def head_plan(*, h_ptr: int, labels_ptr: int, w_last_ptr: int, b_last_ptr: int, dpre_ptr: int, result_ptr: int,
               B: int, B_pad: int, H: int, num_classes: int, loss_kind: int, act_bf16: bool,
               push: Optional[N.PushTarget] = None, push_bh: Optional[N.PushTarget] = None,
+              push_bl: Optional[N.PushTarget] = None,
               off_w_last: int = 0, off_b_last: int = 0, off_b_hidden: int = 0,
               item_w_last_base: int = 0, item_b_last: int = 0, item_b_hidden_base: int = 0,
               seq_ptr: int = 0, inbox_ptr: int = 0, n_inbox: int = 0, ps_global_step_ptr: int = 0,
@@ -47,6 +49,7 @@ def head_plan(*, h_ptr: int, labels_ptr: int, w_last_ptr: int, b_last_ptr: int, 
     p.h, p.labels, p.w_last, p.b_last, p.dpre = h_ptr, labels_ptr, w_last_ptr, b_last_ptr, dpre_ptr
     p.push = push if push is not None else null_push()
     p.push_bh = push_bh if push_bh is not None else p.push
+    p.push_bl = push_bl if push_bl is not None else p.push
     p.off_w_last, p.off_b_last, p.off_b_hidden = off_w_last, off_b_last, off_b_hidden
     p.item_w_last_base, p.item_b_last, p.item_b_hidden_base = item_w_last_base, item_b_last, item_b_hidden_base
     p.result = result_ptr

@@ -1,0 +1,73 @@
+"""Engine configuration shared by ps and worker tasks."""
+from __future__ import annotations
+
+from dataclasses import dataclass, asdict
+
+from .. import _native as N
+
+
+@dataclass(frozen=True)
+class OptimizerConfig:
+    """Reference: `tf.train.AdamOptimizer(FLAGS.learning_rate)` with TF defaults (DS:102); SGD is the
+    north-star "async-SGD" variant."""
+    kind: str = "adam"          # "adam" | "sgd"
+    lr: float = 1e-4            # --learning_rate default (DS:15)
+    beta1: float = 0.9
+    beta2: float = 0.999
+    eps: float = 1e-8
+
+    @property
+    def native_kind(self) -> int:
+        if self.kind == "adam":
+            return N.OPT_ADAM
+        if self.kind == "sgd":
+            return N.OPT_SGD
+        raise ValueError(f"unknown optimizer {self.kind!r} (adam | sgd)")
+
+
+@dataclass(frozen=True)
+class EngineConfig:
+    backend: str = "cuda"            # "cuda" (sm_100a kernels over NVLink peer memory) | "cpu" (shm plumbing backend)
+    dtype: str = "fp32"              # compute dtype of the dense layers: "fp32" (tf32 tensor cores) | "bf16"
+    nslots: int = 2                  # mailbox slots per worker (pushes in flight before the worker waits for an ack)
+    apply_mode: str = "per_push"     # "per_push" (reference semantics) | "merged"
+    push_mode: str = "mailbox"       # "mailbox" (PS kernel applies; Adam or SGD) | "atomic" (SGD red.add, no PS kernel)
+    sharding: str = "round_robin"    # "round_robin" (reference parity) | "byte_balanced"
+    ps_ctas: int = 32                # CTAs of the persistent PS kernel
+    pipeline_slots: int = 4          # worker executor ring depth
+    colocate: bool = False           # worker i shares GPU i with ps i (N workers on N GPUs)
+
+    @property
+    def native_dtype(self) -> int:
+        if self.dtype == "fp32":
+            return N.DT_F32
+        if self.dtype == "bf16":
+            return N.DT_BF16
+        raise ValueError(f"unknown dtype {self.dtype!r} (fp32 | bf16)")
+
+    @property
+    def native_apply_mode(self) -> int:
+        if self.apply_mode == "per_push":
+            return N.APPLY_PER_PUSH
+        if self.apply_mode == "merged":
+            return N.APPLY_MERGED
+        raise ValueError(f"unknown apply_mode {self.apply_mode!r}")
+
+    def validate(self, opt: OptimizerConfig) -> None:
+        if self.backend not in ("cuda", "cpu"):
+            raise ValueError(f"unknown backend {self.backend!r}")
+        if self.push_mode not in ("mailbox", "atomic"):
+            raise ValueError(f"unknown push_mode {self.push_mode!r}")
+        if self.push_mode == "atomic":
+            if opt.kind != "sgd":
+                raise ValueError("push_mode='atomic' fuses the push with an SGD apply (red.add); use --optimizer sgd")
+            if self.dtype != "fp32":
+                raise ValueError("push_mode='atomic' updates only the fp32 master copy; use dtype fp32")
+            if self.backend != "cuda":
+                raise ValueError("push_mode='atomic' needs the cuda backend")
+        if self.nslots < 1:
+            raise ValueError("nslots must be >= 1")
+        _ = self.native_dtype, self.native_apply_mode, opt.native_kind
+
+    def as_dict(self) -> dict:
+        return asdict(self)

@@ -1,0 +1,293 @@
+"""The parameter-server task.
+
+Reference parity (`/root/reference/distributed_server-basic.py`):
+  * DS:80-83   `server = tf.train.Server(...)`; `if job_name == 'ps': server.join()` — a passive process that
+               holds the variables, the Adam slots and `global_step` (DS:88-91, 102-103) and executes the
+               optimizer apply ops the workers' sessions dispatch to it. It never exits on its own.
+
+Here the shard lives in one GPU's HBM (or in POSIX shm for the CPU backend); a *persistent kernel*
+(`ps_serve_kernel`, csrc/ps_apply_sm100.cu) — or the native host loop for the CPU backend — polls the
+workers' mailbox flags and applies. The Python object only allocates, publishes the peer-memory descriptor,
+attaches workers as they register, and blocks in `join()`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+import time
+from typing import Dict, List, Optional
+
+import torch
+
+from .. import _native as N
+from ..cluster import ClusterSpec, Rendezvous
+from ..models.mlp import MLPSpec
+from .config import EngineConfig, OptimizerConfig
+from .peer_mem import Carver, Segment
+from .sharding import ModelLayout, ShardLayout, build_layout
+
+CTRL_GLOBAL_STEP = 0
+CTRL_HOST_STOP = 1
+CTRL_EXIT_COUNTER = 2
+CTRL_WORKER_DONE = 16
+CTRL_WORDS = 64
+
+
+def shard_carver(shard: ShardLayout, n_workers: int, nslots: int) -> Carver:
+    """Byte layout of one PS shard segment (both sides derive pointers from the exported table)."""
+    a = shard.arena_elems
+    ni = max(shard.n_items, 1)
+    c = Carver()
+    c.add("params", a * 4)
+    c.add("adam_m", a * 4)
+    c.add("adam_v", a * 4)
+    c.add("shadow", a * 2)
+    c.add("mailbox", n_workers * nslots * a * 4)
+    c.add("flags", n_workers * nslots * ni * 4)
+    c.add("next_seq", n_workers * ni * 4)
+    c.add("consumed", n_workers * nslots * 4)
+    c.add("items", ni * C.sizeof(N.PsItem))
+    c.add("item_state", ni * C.sizeof(N.PsItemState))
+    c.add("ctrl", CTRL_WORDS * 4)
+    c.add("inbox_table", N.MAX_WORKERS * 8)
+    return c
+
+
+class ParameterServer:
+    def __init__(self, cluster: ClusterSpec, task_index: int, spec: MLPSpec, opt: OptimizerConfig,
+                 cfg: EngineConfig, device: int = 0, rdv: Optional[Rendezvous] = None,
+                 layout: Optional[ModelLayout] = None, verbose: bool = False):
+        cfg.validate(opt)
+        if cluster.num_workers > N.MAX_WORKERS:
+            raise ValueError(f"at most {N.MAX_WORKERS} workers per ps shard")
+        self.cluster, self.task_index, self.spec, self.opt, self.cfg = cluster, task_index, spec, opt, cfg
+        self.device = device if cfg.backend == "cuda" else -1
+        self.verbose = verbose
+        self.layout = layout or build_layout(spec, cluster.num_ps, cfg.sharding)
+        self.shard = self.layout.shards[task_index]
+        self.rdv = rdv or Rendezvous(cluster, "ps", task_index)
+        self.n_workers = cluster.num_workers
+        self.lib = N.lib()
+        self._attached: Dict[int, Segment] = {}
+        self._serving = False
+        self._cpu_handle = None
+        self._stream = None
+        self._ctl_stream = None
+        self._pin = None
+        self._cpu_table = (C.c_void_p * N.MAX_WORKERS)() if cfg.backend == "cpu" else None
+        self._lock = threading.Lock()
+
+        kind = "cuda" if cfg.backend == "cuda" else "shm"
+        if kind == "cuda":
+            N.check(self.lib.dm_set_device(self.device), "set device")
+        carver = shard_carver(self.shard, self.n_workers, cfg.nslots)
+        self.seg = Segment.create(kind, carver.total, device=self.device, table=carver.table(), tag=f"ps{task_index}")
+        self._init_tables()
+        desc = self.seg.export()
+        desc.update({
+            "arena_elems": self.shard.arena_elems, "n_items": self.shard.n_items, "nslots": cfg.nslots,
+            "n_workers": self.n_workers, "owns_global_step": self.shard.owns_global_step,
+        })
+        self.rdv.put(f"ps/{task_index}/segment", desc)
+
+    # ------------------------------------------------------------------------------------------
+    def _host_write(self, region: str, data: bytes, byte_offset: int = 0) -> None:
+        """Synchronous host -> segment write (setup time only)."""
+        if self.cfg.backend == "cuda":
+            buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+            N.check(self.lib.dm_memcpy_async(self.seg.addr(region, byte_offset), C.addressof(buf), len(data), None))
+            N.check(self.lib.dm_stream_sync(None))
+        else:
+            C.memmove(self.seg.addr(region, byte_offset), data, len(data))
+
+    def _init_tables(self) -> None:
+        sh = self.shard
+        ni = max(sh.n_items, 1)
+        items = (N.PsItem * ni)()
+        for i, it in enumerate(sh.items):
+            items[i].offset, items[i].rows, items[i].cols, items[i].ld = it.offset, it.rows, it.cols, it.ld
+            items[i].flags = 1 if (it.shadow and self.cfg.dtype == "bf16") else 0
+        self._host_write("items", bytes(items))
+        self.reset_optimizer_state()
+        ones = (C.c_uint32 * (self.n_workers * ni))(*([1] * (self.n_workers * ni)))
+        self._host_write("next_seq", bytes(ones))
+
+    def reset_optimizer_state(self) -> None:
+        ni = max(self.shard.n_items, 1)
+        st = (N.PsItemState * ni)()
+        for i in range(ni):
+            st[i].t, st[i].beta1_pow, st[i].beta2_pow = 0, 1.0, 1.0
+        self._host_write("item_state", bytes(st))
+
+    # ------------------------------------------------------------------------------------------
+    def _serve_params(self) -> N.PsServeParams:
+        s, sh, cfg, opt = self.seg, self.shard, self.cfg, self.opt
+        P = N.PsServeParams()
+        P.params, P.adam_m, P.adam_v = s.addr("params"), s.addr("adam_m"), s.addr("adam_v")
+        P.shadow_bf16 = s.addr("shadow") if cfg.dtype == "bf16" else None
+        P.items, P.item_state = s.addr("items"), s.addr("item_state")
+        P.n_items, P.n_workers, P.nslots = sh.n_items, self.n_workers, cfg.nslots
+        P.opt, P.apply_mode = opt.native_kind, cfg.native_apply_mode
+        P.lr, P.beta1, P.beta2, P.eps = opt.lr, opt.beta1, opt.beta2, opt.eps
+        P.mailbox, P.arena_elems = s.addr("mailbox"), sh.arena_elems
+        P.flags, P.next_seq, P.consumed = s.addr("flags"), s.addr("next_seq"), s.addr("consumed")
+        P.global_step = s.addr("ctrl", 4 * CTRL_GLOBAL_STEP)
+        P.host_stop = s.addr("ctrl", 4 * CTRL_HOST_STOP)
+        P.exit_counter = s.addr("ctrl", 4 * CTRL_EXIT_COUNTER)
+        P.worker_done = s.addr("ctrl", 4 * CTRL_WORKER_DONE)
+        if cfg.backend == "cuda":
+            P.inbox_table = s.addr("inbox_table")
+        else:
+            P.inbox_table = C.addressof(self._cpu_table)
+        return P
+
+    def start(self, wait_init: bool = True, timeout_s: Optional[float] = None) -> None:
+        """Begin serving. Waits (like TF's non-chief `ready_op` poll) until the chief has initialised the
+        variables, then launches the serve kernel / loop and announces `ps/<k>/serving`."""
+        if self._serving:
+            return
+        if wait_init:
+            self.rdv.get("init/done", timeout_s)
+        self.attach_registered_workers()
+        if self.cfg.push_mode == "atomic":
+            # async-SGD red.add mode: the worker kernels apply straight into the master copy; the shard is pure
+            # memory + the L2 atomic units, no serve kernel is needed.
+            self._serving = True
+            self.rdv.put(f"ps/{self.task_index}/serving", {"mode": "atomic"})
+            return
+        P = self._serve_params()
+        self._P = P
+        if self.cfg.backend == "cuda":
+            N.check(self.lib.dm_set_device(self.device), "set device")
+            out = C.c_void_p()
+            N.check(self.lib.dm_stream_create(C.byref(out)))
+            self._stream = out.value
+            N.check(self.lib.dm_stream_create(C.byref(out)))
+            self._ctl_stream = out.value
+            N.check(self.lib.dm_host_alloc(4096, C.byref(out)))
+            self._pin = out.value
+            n_ctas = max(1, min(self.cfg.ps_ctas, self.shard.n_items))
+            N.check(self.lib.dm_launch_ps_serve(C.addressof(P), n_ctas, self._stream), "launch ps_serve")
+        else:
+            self._cpu_handle = self.lib.dm_cpu_ps_start(C.addressof(P))
+        self._serving = True
+        self.rdv.put(f"ps/{self.task_index}/serving", {"mode": "mailbox"})
+
+    # ------------------------------------------------------------------------------------------
+    def _patch_table(self, w: int, ptr: int) -> None:
+        if self.cfg.push_mode == "atomic":
+            return
+        if self.cfg.backend == "cuda":
+            if self._serving:
+                # the serve kernel is running: patch through the side stream from pinned memory
+                C.c_uint64.from_address(self._pin + 8 * w).value = ptr
+                N.check(self.lib.dm_memcpy_async(self.seg.addr("inbox_table", 8 * w), self._pin + 8 * w, 8,
+                                                 self._ctl_stream))
+                N.check(self.lib.dm_stream_sync(self._ctl_stream))
+            else:
+                self._host_write("inbox_table", bytes(C.c_uint64(ptr)), 8 * w)
+        else:
+            self._cpu_table[w] = ptr
+
+    def attach_registered_workers(self) -> List[int]:
+        """Map the inbox of every worker that has registered since the last call (late joiners welcome)."""
+        new = []
+        with self._lock:
+            for w in range(self.n_workers):
+                if w in self._attached:
+                    continue
+                desc = self.rdv.try_get(f"worker/{w}/inbox")
+                if desc is None:
+                    continue
+                seg = Segment.open(desc, device=self.device)
+                self._attached[w] = seg
+                ptr = seg.addr("inbox", 8 * desc["inbox_index"][str(self.task_index)]) \
+                    if str(self.task_index) in desc["inbox_index"] else 0
+                if ptr:
+                    self._patch_table(w, ptr)
+                self.rdv.put(f"ps/{self.task_index}/attached/{w}", True)
+                new.append(w)
+        return new
+
+    # ------------------------------------------------------------------------------------------
+    def kernel_running(self) -> bool:
+        if not self._serving or self.cfg.push_mode == "atomic":
+            return False
+        if self.cfg.backend == "cuda":
+            return self.lib.dm_stream_query(self._stream) == 1
+        return self._cpu_handle is not None and self.lib.dm_cpu_ps_running(self._cpu_handle) == 1
+
+    def global_step(self) -> int:
+        if self.cfg.backend == "cuda":
+            host = C.c_uint32(0)
+            stream = self._ctl_stream
+            N.check(self.lib.dm_memcpy_async(C.addressof(host), self.seg.addr("ctrl", 4 * CTRL_GLOBAL_STEP), 4, stream))
+            N.check(self.lib.dm_stream_sync(stream))
+            return host.value
+        return self.lib.dm_load_acquire_u32(self.seg.addr("ctrl", 4 * CTRL_GLOBAL_STEP))
+
+    def stop(self) -> None:
+        """Ask the serve kernel / loop to exit and wait for it."""
+        if not self._serving:
+            return
+        if self.cfg.push_mode != "atomic":
+            if self.cfg.backend == "cuda":
+                C.c_uint32.from_address(self._pin + 1024).value = 1
+                N.check(self.lib.dm_memcpy_async(self.seg.addr("ctrl", 4 * CTRL_HOST_STOP), self._pin + 1024, 4,
+                                                 self._ctl_stream))
+                N.check(self.lib.dm_stream_sync(self._ctl_stream))
+                N.check(self.lib.dm_stream_sync(self._stream), "ps serve kernel")
+            else:
+                self.lib.dm_store_release_u32(self.seg.addr("ctrl", 4 * CTRL_HOST_STOP), 1)
+                self.lib.dm_cpu_ps_join(self._cpu_handle)
+                self._cpu_handle = None
+        self._serving = False
+
+    def restart(self) -> None:
+        """Relaunch the serve kernel / loop after `stop()` (all shard state lives in the segment, so serving
+        resumes exactly where it stopped). Used by the benchmark to bracket timed regions with a full device
+        synchronise, which a running persistent kernel would never let return."""
+        if self._serving:
+            return
+        if self.cfg.push_mode == "atomic":
+            self._serving = True
+            return
+        if self.cfg.backend == "cuda":
+            N.check(self.lib.dm_set_device(self.device), "set device")
+            N.check(self.lib.dm_memset_async(self.seg.addr("ctrl", 4 * CTRL_HOST_STOP), 0, 4, self._ctl_stream))
+            N.check(self.lib.dm_stream_sync(self._ctl_stream))
+            n_ctas = max(1, min(self.cfg.ps_ctas, self.shard.n_items))
+            N.check(self.lib.dm_launch_ps_serve(C.addressof(self._P), n_ctas, self._stream), "launch ps_serve")
+        else:
+            self.lib.dm_store_release_u32(self.seg.addr("ctrl", 4 * CTRL_HOST_STOP), 0)
+            self._cpu_handle = self.lib.dm_cpu_ps_start(C.addressof(self._P))
+        self._serving = True
+
+    def join(self, exit_when_done: bool = False, poll_s: float = 0.05) -> None:
+        """`server.join()` (DS:83): block forever serving. With `exit_when_done` the call returns once every
+        worker has left the session and all their pushes are applied, or when a `shutdown` mark appears."""
+        while True:
+            self.attach_registered_workers()
+            if self.rdv.try_get("shutdown") is not None:
+                break
+            if exit_when_done:
+                if self.cfg.push_mode == "atomic":
+                    if self.rdv.add("session/workers_done", 0) >= self.n_workers:
+                        break
+                elif self._serving and not self.kernel_running():
+                    break
+            time.sleep(poll_s)
+        self.stop()
+
+    def close(self) -> None:
+        self.stop()
+        for seg in self._attached.values():
+            seg.close()
+        self._attached.clear()
+        if self.cfg.backend == "cuda":
+            if self._stream:
+                self.lib.dm_stream_destroy(self._stream)
+                self.lib.dm_stream_destroy(self._ctl_stream)
+                self.lib.dm_host_free(self._pin)
+                self._stream = self._ctl_stream = self._pin = None
+        self.seg.close()

@@ -1,0 +1,107 @@
+"""Measurement helpers: GPU clock/throttle sampling during a timed region, CUDA-event timing.
+
+The reference measures nothing (no timers anywhere in /root/reference — SURVEY §5 "Tracing / profiling");
+the metric of this repo is device-timed steps/sec, so this module is new-build only. The clock sampler follows
+the profiling recipe: `nvidia-smi --query-gpu=... -lms 200` started before the timed region, stopped after,
+summarised as the median SM clock under load plus the set of throttle reasons that were active.
+"""
+from __future__ import annotations
+
+import csv
+import io
+import shutil
+import statistics
+import subprocess
+import tempfile
+import time
+from typing import Dict, List, Optional
+
+import torch
+
+_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+
+class ClockSampler:
+    """Samples nvidia-smi in a subprocess between start() and stop()."""
+
+    def __init__(self, interval_ms: int = 100, gpu_indices: Optional[List[int]] = None):
+        self.interval_ms = interval_ms
+        self.gpu_indices = gpu_indices
+        self._proc = None
+        self._out = None
+
+    def start(self) -> None:
+        if shutil.which("nvidia-smi") is None:
+            return
+        self._out = tempfile.NamedTemporaryFile(mode="w+", suffix=".csv", delete=False)
+        cmd = ["nvidia-smi", f"--query-gpu={_QUERY}", "--format=csv,noheader,nounits", "-lms", str(self.interval_ms)]
+        if self.gpu_indices:
+            cmd += ["-i", ",".join(str(i) for i in self.gpu_indices)]
+        try:
+            self._proc = subprocess.Popen(cmd, stdout=self._out, stderr=subprocess.DEVNULL)
+        except Exception:
+            self._proc = None
+
+    def stop(self) -> Dict:
+        if self._proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(self.interval_ms / 1000.0)
+        self._proc.terminate()
+        try:
+            self._proc.wait(timeout=5)
+        except Exception:
+            self._proc.kill()
+        self._out.flush()
+        self._out.seek(0)
+        text = self._out.read()
+        self._out.close()
+        return summarize_clock_csv(text)
+
+
+def summarize_clock_csv(text: str) -> Dict:
+    sm, smax, power = [], [], []
+    reasons = set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for row in csv.reader(io.StringIO(text)):
+        row = [c.strip() for c in row]
+        if len(row) < 9:
+            continue
+        try:
+            sm.append(float(row[1]))
+            smax.append(float(row[2]))
+            power.append(float(row[3]))
+        except ValueError:
+            continue
+        for name, val in zip(names, row[5:9]):
+            if val.lower().startswith("active"):
+                reasons.add(name)
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    return {
+        "sm_mhz": statistics.median(sm),
+        "sm_max_mhz": max(smax),
+        "power_w_max": max(power) if power else None,
+        "reasons": sorted(reasons),
+        "samples": len(sm),
+    }
+
+
+class StreamTimer:
+    """CUDA-event timer on an arbitrary (raw) stream."""
+
+    def __init__(self, stream_ptr: int, device: int):
+        self.stream = torch.cuda.ExternalStream(stream_ptr, device=device)
+        self.t0 = torch.cuda.Event(enable_timing=True)
+        self.t1 = torch.cuda.Event(enable_timing=True)
+
+    def start(self) -> None:
+        self.t0.record(self.stream)
+
+    def stop(self) -> None:
+        self.t1.record(self.stream)
+
+    def elapsed_ms(self) -> float:
+        self.t1.synchronize()
+        return self.t0.elapsed_time(self.t1)

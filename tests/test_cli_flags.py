@@ -1,0 +1,45 @@
+"""Flag surface / validation parity with the reference CLI (distributed_server-basic.py:9-24, 59-67)."""
+import pytest
+
+from dist_mnist_b200 import cli
+
+
+def test_reference_flags_exist_with_expected_defaults():
+    args = cli.build_parser().parse_args([])
+    assert args.data_dir is None
+    assert args.hidden_units == 100                 # DS:12
+    assert args.learning_rate == pytest.approx(1e-4)  # DS:15
+    assert args.ps_hosts is None and args.worker_hosts is None
+    assert args.job_name is None and args.task_index is None
+    # dead flags of the reference are live here, defaulting to the reference's *effective* values
+    assert args.train_steps == 4000                 # StopAtStepHook(last_step=4000), DS:101
+    assert args.batch_size == 32                    # next_batch(32), DS:111
+    assert args.optimizer == "adam"                 # DS:102
+
+
+def test_flag_forms_absl_style():
+    p = cli.build_parser()
+    a = p.parse_args(["--job_name=worker", "--task_index", "1", "--ps_hosts=127.0.0.1:9910",
+                      "--worker_hosts", "127.0.0.1:9900,127.0.0.1:9901", "--hidden_units=64"])
+    assert (a.job_name, a.task_index, a.hidden_units) == ("worker", 1, 64)
+
+
+def test_validation_messages_and_echo(capsys):
+    with pytest.raises(ValueError, match="Must specify the job name explicitly"):
+        cli.validate_task(None, 0)
+    with pytest.raises(ValueError, match="Must specify the job name explicitly"):
+        cli.validate_task("", 0)
+    with pytest.raises(ValueError, match="Must specify a valid task index"):
+        cli.validate_task("ps", None)
+    with pytest.raises(ValueError, match="Must specify a valid task index"):
+        cli.validate_task("ps", -1)
+    capsys.readouterr()
+    cli.validate_task("worker", 3)
+    out = capsys.readouterr().out.splitlines()
+    assert out == ["job name : worker", "task index : 3"]   # DS:60, DS:65
+
+
+def test_missing_hosts_is_an_error():
+    args = cli.build_parser().parse_args(["--job_name", "ps", "--task_index", "0"])
+    with pytest.raises(ValueError):
+        cli.run(args)

@@ -1,0 +1,88 @@
+"""The README recipe of the reference (1 ps + 2 workers as separate OS processes on 127.0.0.1 ports) on the CPU
+backend: real processes, TCP rendezvous, POSIX-shm peer memory. BASELINE.json config 1 / SURVEY §4 item 2."""
+import os
+import socket
+import subprocess
+import sys
+import time
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SCRIPT = os.path.join(ROOT, "distributed_server-basic.py")
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _spawn(job, idx, ps_hosts, worker_hosts, extra=()):
+    cmd = [sys.executable, SCRIPT, "--job_name", job, "--task_index", str(idx), "--ps_hosts", ps_hosts,
+           "--worker_hosts", worker_hosts, "--backend", "cpu", *extra]
+    env = dict(os.environ, PYTHONPATH=ROOT, PYTHONUNBUFFERED="1")
+    return subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, cwd=ROOT)
+
+
+def _finish(p, timeout):
+    try:
+        out, _ = p.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        p.kill()
+        out, _ = p.communicate()
+        pytest.fail(f"process timed out; output so far:\n{out}")
+    return out
+
+
+@pytest.mark.timeout(180)
+def test_one_ps_two_workers_processes():
+    ps_hosts = f"127.0.0.1:{_free_port()}"
+    worker_hosts = f"127.0.0.1:{_free_port()},127.0.0.1:{_free_port()}"
+    common = ["--train_steps", "300", "--learning_rate", "0.001"]
+    ps = _spawn("ps", 0, ps_hosts, worker_hosts, common + ["--ps_exit_when_done"])
+    time.sleep(0.5)
+    w1 = _spawn("worker", 1, ps_hosts, worker_hosts, common)      # non-chief first: must wait for the chief's init
+    time.sleep(0.5)
+    w0 = _spawn("worker", 0, ps_hosts, worker_hosts, common)
+    out0, out1 = _finish(w0, 120), _finish(w1, 120)
+    outp = _finish(ps, 60)
+    assert w0.returncode == 0, out0
+    assert w1.returncode == 0, out1
+    assert ps.returncode == 0, outp
+    assert out0.splitlines()[:2] == ["job name : worker", "task index : 0"]
+    assert outp.splitlines()[:2] == ["job name : ps", "task index : 0"]
+    logged = [l for l in (out0 + out1).splitlines() if l.startswith("Train step ")]
+    assert logged, (out0, out1)
+    steps = sorted({int(l.split(",")[0].split()[-1]) for l in logged})
+    assert all(s % 100 == 0 for s in steps)
+    losses = [float(l.split("loss: ")[1]) for l in logged]
+    assert min(losses) < 0.05
+
+
+@pytest.mark.timeout(120)
+def test_ps_blocks_forever_like_server_join():
+    """Reference ps never exits (server.join(), DS:83): without --ps_exit_when_done it must still be alive after
+    the only worker has finished."""
+    ps_hosts = f"127.0.0.1:{_free_port()}"
+    worker_hosts = f"127.0.0.1:{_free_port()}"
+    ps = _spawn("ps", 0, ps_hosts, worker_hosts, ["--train_steps", "40"])
+    w0 = _spawn("worker", 0, ps_hosts, worker_hosts, ["--train_steps", "40", "--log_every", "20"])
+    out0 = _finish(w0, 90)
+    assert w0.returncode == 0, out0
+    assert "Train step 20, loss:" in out0 and "Train step 40, loss:" in out0
+    time.sleep(1.0)
+    assert ps.poll() is None, "ps task exited although the reference's ps blocks forever"
+    ps.kill()
+    ps.communicate()
+
+
+def test_bad_invocations():
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, SCRIPT, "--task_index", "0", "--ps_hosts", "a:1", "--worker_hosts", "a:2"],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode != 0 and "Must specify the job name explicitly" in r.stderr
+    r = subprocess.run([sys.executable, SCRIPT, "--job_name", "worker", "--ps_hosts", "a:1", "--worker_hosts", "a:2"],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode != 0 and "Must specify a valid task index" in r.stderr
+    assert "job name : worker" in r.stdout

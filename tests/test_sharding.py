@@ -1,0 +1,50 @@
+import torch
+
+from dist_mnist_b200.models import mlp
+from dist_mnist_b200.parallel import sharding
+
+
+def test_round_robin_matches_replica_device_setter_order():
+    # 2 ps -> global_step->ps0, hid_w->ps1, hid_b->ps0, sm_w->ps1, sm_b->ps0
+    pl = sharding.place_variables(mlp.book_model(), 2, "round_robin")
+    assert pl == {"global_step": 0, "hid_w": 1, "hid_b": 0, "sm_w": 1, "sm_b": 0}
+    assert set(sharding.place_variables(mlp.book_model(), 1).values()) == {0}
+
+
+def test_byte_balanced_spreads_the_big_variables():
+    pl = sharding.place_variables(mlp.wide_model(), 2, "byte_balanced")
+    assert pl["global_step"] == 0
+    assert pl["dense/kernel"] != pl["dense_1/kernel"]   # the two ~1M-element kernels land on different shards
+
+
+def _covered(layout):
+    for sh in layout.shards:
+        cover = torch.zeros(sh.arena_elems, dtype=torch.int32)
+        for it in sh.items:
+            for r in range(it.rows):
+                cover[it.offset + r * it.ld: it.offset + r * it.ld + it.cols] += 1
+        expect = torch.zeros_like(cover)
+        for vl in sh.variables:
+            assert vl.offset % sharding.ALIGN_ELEMS == 0
+            if len(vl.spec.shape) == 2:
+                for r in range(vl.rows):
+                    expect[vl.offset + r * vl.ld: vl.offset + r * vl.ld + vl.cols] += 1
+            else:
+                expect[vl.offset: vl.offset + vl.cols] += 1
+        assert torch.equal(cover, expect), "items must tile every variable exactly once"
+
+
+def test_items_tile_every_variable_exactly_once():
+    for spec in (mlp.book_model(100), mlp.book_model(37), mlp.zhihu_model(), mlp.wide_model()):
+        for nps in (1, 2, 3):
+            for strat in ("round_robin", "byte_balanced"):
+                _covered(sharding.build_layout(spec, nps, strat))
+
+
+def test_book_layout_numbers():
+    lay = sharding.build_layout(mlp.book_model(100), 1)
+    sh = lay.shards[0]
+    # 13 dW tiles (784 / 64 columns) + hid_b + sm_w + sm_b
+    assert sh.n_items == 13 + 1 + 1 + 1
+    assert lay.by_name["hid_w"].ld == 784 and lay.by_name["sm_w"].ld == 100
+    assert mlp.book_model(100).num_params == 79510
