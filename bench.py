@@ -151,18 +151,37 @@ def main(argv=None) -> int:
         if world > 1:
             dist.barrier(device_ids=[local_rank])
 
-    def full_sync():
-        """barrier + torch.cuda.synchronize() on every rank. A running persistent PS kernel would make the device
-        synchronise hang, so ps tasks stop their serve kernel (state stays in HBM), synchronise, and relaunch it."""
+    rdv_any = worker.rdv if worker is not None else ps_list[0].rdv
+    phase = [0]
+
+    def full_sync(restart: bool = True):
+        """barrier + torch.cuda.synchronize() on every rank.
+
+        A resident persistent PS kernel makes a device synchronise hang, and — because CUDA loads kernels lazily —
+        even the *first launch* of any new kernel (an NCCL barrier, a torch op) in that context can deadlock
+        against it. So: workers quiesce (all their pushes acknowledged) and say so through the TCP store; ps tasks
+        then stop their serve kernel (all shard state stays in HBM); only then does every rank run the NCCL
+        barrier + synchronise; finally the ps tasks relaunch the kernel and announce it through the store."""
+        phase[0] += 1
+        ph = phase[0]
         if worker is not None:
             worker.wait_applied()
-        barrier()
+        if world > 1:
+            if worker is not None:
+                rdv_any.add(f"bench/{ph}/quiet", 1)
+            if ps_list:
+                rdv_any.wait_count(f"bench/{ph}/quiet", n_workers)
         for ps in ps_list:
             ps.stop()
-        torch.cuda.synchronize()
-        for ps in ps_list:
-            ps.restart()
         barrier()
+        torch.cuda.synchronize()
+        if restart:
+            for ps in ps_list:
+                ps.restart()
+            if world > 1:
+                if ps_list:
+                    rdv_any.add(f"bench/{ph}/serving", 1)
+                rdv_any.wait_count(f"bench/{ph}/serving", args.num_ps)
 
     elapsed_ms = 0.0
     e2e_s = 0.0
@@ -173,9 +192,7 @@ def main(argv=None) -> int:
         xrow, yrow = dev_x.shape[1] * dev_x.element_size(), dev_y.shape[1] * 4
 
         def resident_steps(n, start):
-            for i in range(n):
-                r = ((start + i) * B) % n_rows
-                worker.submit_resident(dev_x.data_ptr() + r * xrow, dev_y.data_ptr() + r * yrow)
+            worker.run_resident(n, dev_x.data_ptr(), dev_y.data_ptr(), xrow, yrow, n_rows, start)
 
         resident_steps(max(W, 3), 0)
         loader = loaders["l"]
@@ -204,18 +221,18 @@ def main(argv=None) -> int:
         full_sync()
         if worker is not None:
             t0 = time.perf_counter()
-            outs = worker.run_steps(K, loader)
-            worker.wait_applied()
-            torch.cuda.synchronize()
+            outs = worker.run_steps(K, loader)   # drains: every result has been read back on return
+            worker.wait_applied()                # ... and every push of the region is applied on the ps
             e2e_s = time.perf_counter() - t0
             assert len(outs) == K
             h2d_bytes = worker.x_bytes + worker.y_bytes
             d2h_bytes = C.sizeof(N.StepResult)
-        full_sync()
-    clocks = sampler.stop() if sampler else None
+    clocks_stop_needed = sampler is not None
+    final_step = worker.read_global_step() if (worker is not None and worker.is_chief) else 0
+    full_sync(restart=False)   # serve kernels stay down from here on: torch/NCCL ops below are safe
+    clocks = sampler.stop() if clocks_stop_needed else None
 
     # ---------------- reduce over ranks ----------------
-    final_step = worker.read_global_step() if (worker is not None and worker.is_chief) else 0
     kps = worker.kernels_per_step if worker is not None else 0
     stats = torch.tensor([elapsed_ms, e2e_s, float(launches), float(h2d_bytes), float(d2h_bytes), float(final_step),
                           float(kps)], dtype=torch.float64, device="cuda")

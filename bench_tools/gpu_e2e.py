@@ -42,18 +42,26 @@ def wait_gstep(worker, target, timeout=10.0):
         time.sleep(0.0005)
 
 
-def check_traj() -> bool:
+# (model, optimizer, dtype, push mode, #ps, batch, tolerance). SGD is linear in the gradient, so its parameter
+# error directly reflects kernel numerics (tf32 / bf16 rounding); Adam's normalised step m/sqrt(v) turns a
+# rounding-level gradient difference on a near-zero gradient into a full +-lr step, hence the looser bound there.
+TRAJ_CASES = [
+        ("book", "adam", "fp32", "mailbox", 1, 32, 5e-2),
+        ("book", "sgd", "fp32", "mailbox", 1, 32, 2e-2),
+        ("book", "sgd", "fp32", "atomic", 1, 32, 2e-2),
+        ("book", "adam", "fp32", "mailbox", 2, 32, 5e-2),
+        ("zhihu", "sgd", "fp32", "mailbox", 2, 100, 2e-2),
+        ("zhihu", "adam", "fp32", "mailbox", 2, 100, 2.5e-1),
+        ("wide", "sgd", "bf16", "mailbox", 2, 64, 5e-2),
+        ("wide", "adam", "bf16", "mailbox", 2, 64, 2.5e-1),
+        ("book", "adam", "bf16", "mailbox", 1, 32, 2e-1),
+]
+
+
+def check_traj(only=None) -> bool:
     ok = True
     ds = data.synthetic_mnist(4096, seed=3)
-    cases = [
-        ("book", "adam", "fp32", "mailbox", 1, 32, 5e-2),
-        ("book", "sgd", "fp32", "mailbox", 1, 32, 5e-2),
-        ("book", "sgd", "fp32", "atomic", 1, 32, 5e-2),
-        ("book", "adam", "fp32", "mailbox", 2, 32, 5e-2),
-        ("zhihu", "adam", "fp32", "mailbox", 2, 100, 5e-2),
-        ("wide", "adam", "bf16", "mailbox", 2, 64, 2e-1),
-        ("book", "adam", "bf16", "mailbox", 1, 32, 2e-1),
-    ]
+    cases = TRAJ_CASES if only is None else [TRAJ_CASES[only]]
     for (model, okind, dtype, push, nps, batch, tol) in cases:
         name = f"traj model={model} opt={okind} dtype={dtype} push={push} ps={nps} B={batch}"
         try:
@@ -92,13 +100,14 @@ def check_traj() -> bool:
     return ok
 
 
-def check_throughput() -> bool:
+TP_CASES = [("book", "adam", "fp32", "mailbox", 32), ("book", "sgd", "fp32", "atomic", 32),
+            ("book", "sgd", "fp32", "mailbox", 32), ("wide", "adam", "bf16", "mailbox", 32)]
+
+
+def check_throughput(only=None) -> bool:
     ok = True
     ds = data.synthetic_mnist(data.TRAIN_SIZE, seed=0)
-    for (model, okind, dtype, push, batch) in [("book", "adam", "fp32", "mailbox", 32),
-                                                ("book", "sgd", "fp32", "atomic", 32),
-                                                ("book", "sgd", "fp32", "mailbox", 32),
-                                                ("wide", "adam", "bf16", "mailbox", 32)]:
+    for (model, okind, dtype, push, batch) in (TP_CASES if only is None else [TP_CASES[only]]):
         name = f"throughput model={model} opt={okind} dtype={dtype} push={push} B={batch}"
         try:
             spec = mlp.get_model(model)
@@ -135,16 +144,20 @@ def main(argv) -> int:
     which = argv[0] if argv else "all"
     if which == "all":
         rc = 0
-        for g in CHECKS:
-            print(f"===== {g} =====", flush=True)
+        jobs = [f"traj:{i}" for i in range(len(TRAJ_CASES))] + [f"throughput:{i}" for i in range(len(TP_CASES))]
+        for g in jobs:
             try:
-                code = subprocess.run([sys.executable, "-m", "bench_tools.gpu_e2e", g], timeout=400).returncode
+                code = subprocess.run([sys.executable, "-m", "bench_tools.gpu_e2e", g], timeout=120).returncode
             except subprocess.TimeoutExpired:
                 code = 124
-            print(f"===== {g}: exit {code} =====", flush=True)
+            if code != 0:
+                print(f"===== {g}: exit {code} =====", flush=True)
             rc |= int(code != 0)
         return rc
-    return 0 if CHECKS[which]() else 1
+    import faulthandler
+    faulthandler.dump_traceback_later(75, exit=True)  # a hang prints the Python stack of every thread, then exits
+    group, _, idx = which.partition(":")
+    return 0 if CHECKS[group](int(idx) if idx else None) else 1
 
 
 if __name__ == "__main__":

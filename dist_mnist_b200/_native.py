@@ -55,6 +55,8 @@ class GemmParams(C.Structure):
         ("push_offset", C.c_uint64),
         ("push_item_base", C.c_int), ("pad_", C.c_int),
         ("bump_seq", C.c_void_p),
+        ("splitk_scratch", C.c_void_p),
+        ("splitk_counter", C.c_void_p),
     ]
 
 
@@ -186,6 +188,7 @@ def _declare(l: C.CDLL) -> None:
         "dm_exec_result": (i, [vp, u64, vp, i]),
         "dm_exec_drain": (i, [vp]),
         "dm_exec_run": (i, [vp, vp, u64, vp, u32, C.POINTER(u64)]),
+        "dm_exec_run_resident": (i, [vp, u64, vp, vp, sz, sz, u64, u64, u64]),
         "dm_exec_submitted": (u64, [vp]),
         "dm_exec_kernel_launches": (u64, [vp]),
         "dm_exec_destroy": (i, [vp]),

@@ -21,6 +21,9 @@ cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ge
 size_t head_smem_bytes(int B_pad, int H, int C);
 cudaError_t prepare_gemm_kernels();
 cudaError_t prepare_head_kernel();
+cudaError_t preload_head_kernels();
+cudaError_t preload_ps_kernels();
+cudaError_t preload_p2p_kernels();
 cudaError_t launch_head(const HeadParams& p, cudaStream_t stream);
 cudaError_t launch_accuracy(const float* logits, const float* labels, int B, int C, uint32_t* correct,
                             cudaStream_t stream);
@@ -198,6 +201,11 @@ int dm_prepare_kernels(int dev) {
   DM_CUDA(cudaSetDevice(dev));
   DM_CUDA(dm::prepare_gemm_kernels());
   DM_CUDA(dm::prepare_head_kernel());
+  // CUDA loads kernels lazily; a first launch while a persistent PS kernel is resident can deadlock on the
+  // context-wide synchronisation the load needs — so load everything up front.
+  DM_CUDA(dm::preload_head_kernels());
+  DM_CUDA(dm::preload_ps_kernels());
+  DM_CUDA(dm::preload_p2p_kernels());
   return 0;
 }
 

@@ -295,6 +295,20 @@ int dm_exec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uint
   return 0;
 }
 
+// Native loop over a *device-resident* dataset (benchmark "kernel-side" number): step i takes the batch of
+// `batch_rows` consecutive rows starting at ((start + i) * batch_rows) % n_rows; inputs reach the slot buffers
+// with a device-to-device copy on the copy stream (overlapped with the previous step's kernels).
+int dm_exec_run_resident(void* h, uint64_t n_steps, const void* x_base, const void* y_base, size_t x_row_bytes,
+                         size_t y_row_bytes, uint64_t n_rows, uint64_t batch_rows, uint64_t start) {
+  const uint8_t* xb = static_cast<const uint8_t*>(x_base);
+  const uint8_t* yb = static_cast<const uint8_t*>(y_base);
+  for (uint64_t i = 0; i < n_steps; ++i) {
+    const uint64_t r = ((start + i) * batch_rows) % n_rows;
+    if (dm_exec_submit(h, xb + r * x_row_bytes, yb + r * y_row_bytes, nullptr) != 0) return -1;
+  }
+  return 0;
+}
+
 uint64_t dm_exec_submitted(void* h) { return static_cast<Executor*>(h)->submitted; }
 uint64_t dm_exec_kernel_launches(void* h) { return static_cast<Executor*>(h)->launches; }
 

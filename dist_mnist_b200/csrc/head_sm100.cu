@@ -12,26 +12,42 @@
 //   db_hid = sum_B dpre
 // and pushes dW_last / db_last / db_hid to the parameter server (mailbox + flags, or red.add for SGD).
 //
-// grid = ceil(H / 128) CTAs x 256 threads. Every CTA recomputes the (tiny) logits/softmax phase and then
+// grid = ceil(H / 128) CTAs x 512 threads. Every CTA recomputes the (tiny) logits/softmax phase and then
 // owns a 128-wide slice of H for the gradient phase, so no inter-CTA synchronisation is needed.
+// The kernel is latency- not throughput-bound (~0.2 MFLOP), so it is organised to keep every phase a handful
+// of dependent instructions deep: operands are staged in shared memory once, all global loads of a phase are
+// independent, 16 warps hide the shared-memory latency.
 // Replaces reference ops DS:52-53 + their gradients from DS:103 (part of K6, K12).
 #include "common.cuh"
 #include "protocol.h"
 
 namespace dm {
 
-constexpr int kHeadThreads = 256;
+constexpr int kHeadThreads = 512;
 constexpr int kHeadSlice = 128;
+constexpr int kHeadGroups = kHeadThreads / kHeadSlice;  // batch-row groups in the gradient phase
 constexpr int kMaxC = 16;
 constexpr int kMaxB = 256;
+constexpr int kPartStride = kMaxC + 1;
 
-__device__ __forceinline__ float ld_act(const void* p, size_t idx, int is_bf16) {
+__device__ __forceinline__ float ld_act(const void* __restrict__ p, size_t idx, int is_bf16) {
   return is_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[idx])
                  : reinterpret_cast<const float*>(p)[idx];
 }
-__device__ __forceinline__ void st_act(void* p, size_t idx, int is_bf16, float v) {
+__device__ __forceinline__ void st_act(void* __restrict__ p, size_t idx, int is_bf16, float v) {
   if (is_bf16) reinterpret_cast<__nv_bfloat16*>(p)[idx] = __float2bfloat16(v);
   else reinterpret_cast<float*>(p)[idx] = v;
+}
+// 4 consecutive activations (16-byte aligned for fp32, 8-byte for bf16)
+__device__ __forceinline__ float4 ld_act4(const void* __restrict__ p, size_t idx, int is_bf16) {
+  if (is_bf16) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p) + idx);
+    const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+    const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+    const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + idx);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -58,20 +74,32 @@ __device__ __forceinline__ void push_value(const PushTarget& t, float* dst, floa
   else *dst = v;
 }
 
-__global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_constant__ HeadParams p) {
-  extern __shared__ float hsm[];
-  // smem carve-up
-  float* sW = hsm;                         // [C][H]
-  float* sLogit = sW + p.C * p.H;          // [B][kMaxC]  logits -> dlogits
-  float* sRed = sLogit + p.B_pad * kMaxC;  // [32] block reductions
-  float* sPart = sRed + 64;                // [2][kHeadSlice][kMaxC + 1] dW/db partials of the second b-half
+// shared-memory row stride of W_last: multiple of 4 floats with (stride/4) odd, so that the 16 class rows
+// read by one half-warp land in distinct bank groups.
+__host__ __device__ __forceinline__ int head_w_stride(int H) {
+  int s = (H + 3) & ~3;
+  if (((s >> 2) & 1) == 0) s += 4;
+  return s;
+}
 
+__global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_constant__ HeadParams p) {
+  extern __shared__ __align__(16) float hsm[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int C = p.C, H = p.H, B = p.B;
+  const int ldw = head_w_stride(H);
+  const int h0 = blockIdx.x * kHeadSlice;
 
+  // smem carve-up. region0 holds W_last, later (gradient phase) the cross-group partial sums.
+  const int region0 = max(kMaxC * ldw, (kHeadGroups - 1) * kHeadSlice * kPartStride);
+  float* sW = hsm;                               // [kMaxC][ldw] (rows >= C are zero)
+  float* sPart = hsm;                            // aliases sW once the W columns are in registers
+  float* sLogit = hsm + region0;                 // [B_pad][kMaxC] logits, then dlogits
+  float* sHs = sLogit + p.B_pad * kMaxC;         // [B_pad][kHeadSlice] this CTA's slice of h
+  float* sRed = sHs + p.B_pad * kHeadSlice;      // [64] block reductions
   __shared__ uint32_t s_seq;
   __shared__ uint32_t s_gstep;
+
   if (tid == 0) {
     uint32_t seq = p.seq_ptr ? *reinterpret_cast<volatile uint32_t*>(p.seq_ptr) : 1u;
     s_seq = seq;
@@ -101,30 +129,41 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
     s_gstep = gstep;
   }
 
-  // ---- phase 1: W_last -> smem, logits for every row (each CTA recomputes; it is tiny) ----
-  for (int i = tid; i < C * H; i += kHeadThreads) sW[i] = p.w_last[i];
+  // ---- phase A: stage W_last (peer loads from the PS shard) and this CTA's slice of h ----
+  for (int i = tid; i < kMaxC * ldw; i += kHeadThreads) {
+    const int c = i / ldw, k = i - c * ldw;
+    sW[i] = (c < C && k < H) ? p.w_last[static_cast<size_t>(c) * H + k] : 0.f;
+  }
+  for (int i = tid; i < p.B_pad * kHeadSlice; i += kHeadThreads) {
+    const int b = i / kHeadSlice, hh = i - b * kHeadSlice;
+    sHs[i] = (b < B && h0 + hh < H) ? ld_act(p.h, static_cast<size_t>(b) * p.ldh + h0 + hh, p.act_bf16) : 0.f;
+  }
   __syncthreads();
   const uint32_t seq = s_seq;
 
-  for (int b = warp; b < B; b += kHeadThreads / 32) {
-    float acc[kMaxC];
-#pragma unroll
-    for (int c = 0; c < kMaxC; ++c) acc[c] = 0.f;
-    for (int h = lane; h < H; h += 32) {
-      const float hv = ld_act(p.h, static_cast<size_t>(b) * p.ldh + h, p.act_bf16);
-#pragma unroll
-      for (int c = 0; c < kMaxC; ++c)
-        if (c < C) acc[c] = fmaf(hv, sW[c * H + h], acc[c]);
-    }
-#pragma unroll
-    for (int c = 0; c < kMaxC; ++c) {
-      const float s = warp_sum(acc[c]);
-      if (lane == 0 && c < C) sLogit[b * kMaxC + c] = s + p.b_last[c];
+  // ---- phase B: logits. thread -> (row b, class c); 16 lanes share a row (broadcast loads of h) ----
+  {
+    const int c = tid & (kMaxC - 1);
+    const float bias = c < C ? p.b_last[c] : 0.f;
+    const float* wrow = sW + c * ldw;
+    const int H4 = ((p.ldh & 3) == 0) ? (H & ~3) : 0;
+    for (int b = tid / kMaxC; b < B; b += kHeadThreads / kMaxC) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const size_t rowoff = static_cast<size_t>(b) * p.ldh;
+#pragma unroll 4
+      for (int k = 0; k < H4; k += 4) {
+        const float4 hv = ld_act4(p.h, rowoff + k, p.act_bf16);
+        const float4 wv = *reinterpret_cast<const float4*>(wrow + k);
+        a0 = fmaf(hv.x, wv.x, a0); a1 = fmaf(hv.y, wv.y, a1);
+        a2 = fmaf(hv.z, wv.z, a2); a3 = fmaf(hv.w, wv.w, a3);
+      }
+      for (int k = H4; k < H; ++k) a0 = fmaf(ld_act(p.h, rowoff + k, p.act_bf16), wrow[k], a0);
+      sLogit[b * kMaxC + c] = (a0 + a1) + (a2 + a3) + bias;
     }
   }
   __syncthreads();
 
-  // ---- phase 2: softmax / loss / accuracy / dlogits, one thread per row ----
+  // ---- phase C: softmax / loss / accuracy / dlogits, one thread per row ----
   float loss_part = 0.f;
   float corr_part = 0.f;
   for (int b = tid; b < B; b += kHeadThreads) {
@@ -137,6 +176,11 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
       if (c < C) {
         z[c] = sLogit[b * kMaxC + c];
         y[c] = p.labels[static_cast<size_t>(b) * C + c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) {
+      if (c < C) {
         if (z[c] > zmax) { zmax = z[c]; zarg = c; }
         if (y[c] > ybest) { ybest = y[c]; yarg = c; }
         ysum += y[c];
@@ -167,17 +211,15 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
       }
 #pragma unroll
       for (int c = 0; c < kMaxC; ++c)
-        if (c < C) { const float pc = e[c] * inv; sLogit[b * kMaxC + c] = pc * (g[c] - gp); }
+        sLogit[b * kMaxC + c] = c < C ? (e[c] * inv) * (g[c] - gp) : 0.f;
     } else {
       // L = (1/B) sum_b -sum_c y*log_softmax(z);  dz = (p*sum(y) - y)/B
       const float k = 1.f / static_cast<float>(B);
       const float lse = zmax + __logf(esum);
 #pragma unroll
       for (int c = 0; c < kMaxC; ++c) {
-        if (c < C) {
-          loss_part -= k * y[c] * (z[c] - lse);
-          sLogit[b * kMaxC + c] = k * (e[c] * inv * ysum - y[c]);
-        }
+        if (c < C) loss_part -= k * y[c] * (z[c] - lse);
+        sLogit[b * kMaxC + c] = c < C ? k * (e[c] * inv * ysum - y[c]) : 0.f;
       }
     }
   }
@@ -185,7 +227,17 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
   loss_part = warp_sum(loss_part);
   corr_part = warp_sum(corr_part);
   if (lane == 0) { sRed[warp] = loss_part; sRed[32 + warp] = corr_part; }
+
+  // this thread's column of W_last, before region0 is recycled for the partial sums
+  const int hh = tid & (kHeadSlice - 1);
+  const int grp = tid >> 7;  // kHeadGroups groups split the batch rows
+  const int h = h0 + hh;
+  const bool h_ok = h < H;
+  float wcol[kMaxC];
+#pragma unroll
+  for (int c = 0; c < kMaxC; ++c) wcol[c] = sW[c * ldw + min(h, H - 1)];
   __syncthreads();
+
   if (blockIdx.x == 0 && tid == 0) {
     float l = 0.f, cr = 0.f;
     for (int w = 0; w < kHeadThreads / 32; ++w) { l += sRed[w]; cr += sRed[32 + w]; }
@@ -201,76 +253,83 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
   }
   if (!p.compute_grads) return;
 
-  // ---- phase 3: gradients for this CTA's 128-wide slice of H ----
-  const int hh = tid & (kHeadSlice - 1);
-  const int half = tid >> 7;  // two halves split the batch rows
-  const int h = blockIdx.x * kHeadSlice + hh;
-  const bool h_ok = h < H;
-  float wcol[kMaxC], dw[kMaxC];
+  // ---- phase D: gradients for this CTA's 128-wide slice of H; thread -> (column hh, row group grp) ----
+  float dw[kMaxC];
 #pragma unroll
-  for (int c = 0; c < kMaxC; ++c) { wcol[c] = (h_ok && c < C) ? sW[c * H + h] : 0.f; dw[c] = 0.f; }
+  for (int c = 0; c < kMaxC; ++c) dw[c] = 0.f;
   float dbh = 0.f;
-  const int bhalf = (B + 1) / 2;
-  const int b_lo = half == 0 ? 0 : bhalf;
-  const int b_hi = half == 0 ? bhalf : B;
-  for (int b = b_lo; b < b_hi; ++b) {
-    float hv = 0.f;
-    if (h_ok) hv = ld_act(p.h, static_cast<size_t>(b) * p.ldh + h, p.act_bf16);
+  for (int b = grp; b < B; b += kHeadGroups) {
+    const float hv = sHs[b * kHeadSlice + hh];
+    const float4* dl4 = reinterpret_cast<const float4*>(sLogit + b * kMaxC);  // broadcast reads
     float dh = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxC; ++c) {
-      if (c < C) {
-        const float dl = sLogit[b * kMaxC + c];
-        dw[c] = fmaf(dl, hv, dw[c]);
-        dh = fmaf(dl, wcol[c], dh);
-      }
+    for (int c4 = 0; c4 < kMaxC / 4; ++c4) {
+      const float4 d = dl4[c4];
+      dw[4 * c4 + 0] = fmaf(d.x, hv, dw[4 * c4 + 0]); dh = fmaf(d.x, wcol[4 * c4 + 0], dh);
+      dw[4 * c4 + 1] = fmaf(d.y, hv, dw[4 * c4 + 1]); dh = fmaf(d.y, wcol[4 * c4 + 1], dh);
+      dw[4 * c4 + 2] = fmaf(d.z, hv, dw[4 * c4 + 2]); dh = fmaf(d.z, wcol[4 * c4 + 2], dh);
+      dw[4 * c4 + 3] = fmaf(d.w, hv, dw[4 * c4 + 3]); dh = fmaf(d.w, wcol[4 * c4 + 3], dh);
     }
     const float dp = hv > 0.f ? dh : 0.f;
     dbh += dp;
     if (h_ok) st_act(p.dpre, static_cast<size_t>(b) * p.ldh + h, p.act_bf16, dp);
   }
   // zero the padding rows of dpre so the dW GEMM's batch reduction sees zeros
-  for (int b = B + half; b < p.B_pad; b += 2)
+  for (int b = B + grp; b < p.B_pad; b += kHeadGroups)
     if (h_ok) st_act(p.dpre, static_cast<size_t>(b) * p.ldh + h, p.act_bf16, 0.f);
 
-  if (half == 1) {
+  if (grp > 0) {
+    float* dst = sPart + ((grp - 1) * kHeadSlice + hh) * kPartStride;
 #pragma unroll
-    for (int c = 0; c < kMaxC; ++c) sPart[hh * (kMaxC + 1) + c] = dw[c];
-    sPart[hh * (kMaxC + 1) + kMaxC] = dbh;
+    for (int c = 0; c < kMaxC; ++c) dst[c] = dw[c];
+    dst[kMaxC] = dbh;
   }
   __syncthreads();
   const ResolvedPushH r = resolve_push_h(p.push, seq);
   const ResolvedPushH rb = resolve_push_h(p.push_bh, seq);
   const ResolvedPushH rl = resolve_push_h(p.push_bl, seq);
-  if (half == 0 && h_ok) {
+  if (grp == 0 && h_ok) {
+#pragma unroll
+    for (int g = 0; g < kHeadGroups - 1; ++g) {
+      const float* src = sPart + (g * kHeadSlice + hh) * kPartStride;
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c) dw[c] += src[c];
+      dbh += src[kMaxC];
+    }
 #pragma unroll
     for (int c = 0; c < kMaxC; ++c)
-      if (c < C) push_value(p.push, r.base + p.off_w_last + static_cast<size_t>(c) * H + h,
-                            dw[c] + sPart[hh * (kMaxC + 1) + c]);
-    push_value(p.push_bh, rb.base + p.off_b_hidden + h, dbh + sPart[hh * (kMaxC + 1) + kMaxC]);
+      if (c < C) push_value(p.push, r.base + p.off_w_last + static_cast<size_t>(c) * H + h, dw[c]);
+    push_value(p.push_bh, rb.base + p.off_b_hidden + h, dbh);
   }
-  if (blockIdx.x == 0 && half == 1 && hh < C) {
-    float s = 0.f;
-    for (int b = 0; b < B; ++b) s += sLogit[b * kMaxC + hh];
-    push_value(p.push_bl, rl.base + p.off_b_last + hh, s);
+  if (blockIdx.x == 0 && grp == 1 && hh < C) {
+    float s0 = 0.f, s1 = 0.f;
+    int b = 0;
+    for (; b + 1 < B; b += 2) { s0 += sLogit[b * kMaxC + hh]; s1 += sLogit[(b + 1) * kMaxC + hh]; }
+    if (b < B) s0 += sLogit[b * kMaxC + hh];
+    push_value(p.push_bl, rl.base + p.off_b_last + hh, s0 + s1);
   }
   if (p.push.mode == PUSH_MAILBOX) {
-    __threadfence_system();
+    // the CTA barrier orders every thread's P2P stores before thread 0's cumulative system-scope release
     __syncthreads();
     if (tid == 0) {
-      st_release_sys_u32(r.flags + p.item_w_last_base + blockIdx.x, seq);
-      st_release_sys_u32(rb.flags + p.item_b_hidden_base + blockIdx.x, seq);
-      if (blockIdx.x == 0) st_release_sys_u32(rl.flags + p.item_b_last, seq);
+      fence_acq_rel_sys();
+      st_relaxed_sys_u32(r.flags + p.item_w_last_base + blockIdx.x, seq);
+      st_relaxed_sys_u32(rb.flags + p.item_b_hidden_base + blockIdx.x, seq);
+      if (blockIdx.x == 0) st_relaxed_sys_u32(rl.flags + p.item_b_last, seq);
     }
   }
 }
 
 size_t head_smem_bytes(int B_pad, int H, int C) {
-  return sizeof(float) * (static_cast<size_t>(C) * H + static_cast<size_t>(B_pad) * kMaxC + 64 +
-                          static_cast<size_t>(kHeadSlice) * (kMaxC + 1));
+  (void)C;
+  const int ldw = head_w_stride(H);
+  const size_t region0 = static_cast<size_t>(
+      kMaxC * ldw > (kHeadGroups - 1) * kHeadSlice * kPartStride ? kMaxC * ldw
+                                                                 : (kHeadGroups - 1) * kHeadSlice * kPartStride);
+  return sizeof(float) * (region0 + static_cast<size_t>(B_pad) * kMaxC + static_cast<size_t>(B_pad) * kHeadSlice + 64);
 }
 
-constexpr int kHeadMaxSmem = 200 * 1024;
+constexpr int kHeadMaxSmem = 224 * 1024;
 
 cudaError_t prepare_head_kernel() {
   return cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHeadMaxSmem);
@@ -331,6 +390,14 @@ cudaError_t launch_accuracy(const float* logits, const float* labels, int B, int
   if (blocks < 1) blocks = 1;
   accuracy_kernel<<<blocks, threads, 0, stream>>>(logits, labels, B, C, correct);
   return cudaGetLastError();
+}
+
+cudaError_t preload_head_kernels() {
+  cudaFuncAttributes a;
+  cudaError_t e;
+  if ((e = cudaFuncGetAttributes(&a, head_kernel)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&a, accuracy_kernel)) != cudaSuccess) return e;
+  return cudaSuccess;
 }
 
 }  // namespace dm

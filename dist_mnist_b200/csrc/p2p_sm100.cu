@@ -144,3 +144,15 @@ cudaError_t launch_pingpong(uint32_t* local_flag, uint32_t* remote_flag, int ite
 }
 
 }  // namespace dm
+
+namespace dm {
+cudaError_t preload_p2p_kernels() {
+  cudaFuncAttributes a;
+  cudaError_t e;
+  if ((e = cudaFuncGetAttributes(&a, p2p_copy_ldst_kernel)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&a, p2p_copy_tma_kernel)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&a, p2p_reduce_apply_kernel)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&a, pingpong_kernel)) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+}  // namespace dm

@@ -67,6 +67,8 @@ struct GemmParams {
   int push_item_base;   // first flag item index for this variable's tiles (tile = mtile * ntiles + ntile)
   int pad_;
   uint32_t* bump_seq;   // if set, CTA (0,0,0) increments it: the first kernel of a step opens a new push seq
+  float* splitk_scratch;     // gridDim.z > 1: [mtiles][splits][128][bn] fp32 partial tiles
+  uint32_t* splitk_counter;  // gridDim.z > 1: [mtiles] arrival counters (self-resetting)
 };
 
 // Softmax-cross-entropy head (last dense layer + loss + its gradients), see head_sm100.cu

@@ -194,10 +194,13 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
       __syncthreads();
     }
     // ---- exit protocol: host stop request, or every worker has left and all their pushes are applied ----
+    // (checked every 32nd poll round only: the check itself costs several system-scope loads, and the poll
+    //  loop's period is the PS's reaction latency)
     if (tid == 0) {
       uint32_t ex = 0;
-      if ((iter & 15u) == 0u && *P.host_stop != 0u) ex = 1;
-      if (!ex) {
+      const bool check = (iter & 31u) == 0u;
+      if (check && *P.host_stop != 0u) ex = 1;
+      if (check && !ex) {
         bool all_done = true;
         for (int w = 0; w < P.n_workers && all_done; ++w) {
           const uint32_t d = ld_acquire_sys_u32(P.worker_done + w);  // = last push seq + 1, 0 while active
@@ -312,4 +315,20 @@ cudaError_t launch_worker_done(uint32_t* done_slot, const uint32_t* seq_ptr, cud
   return cudaGetLastError();
 }
 
+}  // namespace dm
+
+namespace dm {
+// Force-load every kernel of this translation unit. With CUDA's lazy module loading the *first* launch of a
+// kernel may need a context-wide synchronisation; if that first launch happens while the persistent serve
+// kernel is resident (and the serve kernel is waiting for the new kernel's flags) the process deadlocks.
+cudaError_t preload_ps_kernels() {
+  cudaFuncAttributes a;
+  cudaError_t e;
+  if ((e = cudaFuncGetAttributes(&a, ps_serve_kernel)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&a, dense_apply_kernel)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&a, shadow_refresh_kernel)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&a, wait_ack_kernel)) != cudaSuccess) return e;
+  if ((e = cudaFuncGetAttributes(&a, worker_done_kernel)) != cudaSuccess) return e;
+  return cudaSuccess;
+}
 }  // namespace dm

@@ -71,6 +71,8 @@ class GemmPlan:
     splits: int
     grid: tuple
     name: str = "gemm"
+    scratch: object = None    # split-K partial tiles (kept alive with the plan)
+    counters: object = None
 
     def launch(self, stream: Optional[int] = None) -> None:
         s = N.current_stream_ptr() if stream is None else stream
@@ -93,6 +95,26 @@ def _pick_stages(bn: int, kc: int) -> int:
     return max(1, min(MAX_STAGES, kc, SMEM_BUDGET // stage))
 
 
+def auto_splits(K: int, dtype: int, mtiles: int) -> int:
+    """Split-K factor for the K-loop GEMMs (forward, dX). One SM's TMA front-end moves 128-byte-wide boxes at
+    only ~16 B/clk, so a long K loop is spread over several CTAs (<= 2 k-chunks each) whose partial tiles are
+    summed by the last-arriving CTA. Bounded so that the grid stays well inside one wave of 148 SMs."""
+    kc = ceil_div(K, bke(dtype))
+    return max(1, min(16, ceil_div(kc, 2), max(1, 96 // max(1, mtiles))))
+
+
+def _attach_splitk(plan: "GemmPlan", mtiles: int, splits: int, bn: int) -> None:
+    if splits <= 1:
+        return
+    import torch
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    plan.scratch = torch.zeros(mtiles * splits * TILE_M * bn, dtype=torch.float32, device=dev)
+    plan.counters = torch.zeros(mtiles, dtype=torch.int32, device=dev)
+    plan.params.splitk_scratch = plan.scratch.data_ptr()
+    plan.params.splitk_counter = plan.counters.data_ptr()
+
+
 def _base_params(M, N_, K, bn, dtype, splits) -> N.GemmParams:
     p = N.GemmParams()
     p.M, p.N, p.K = M, N_, K
@@ -108,7 +130,8 @@ def _base_params(M, N_, K, bn, dtype, splits) -> N.GemmParams:
 
 def forward_plan(*, w_ptr: int, x_ptr: int, out_ptr: int, bias_ptr: int, O: int, I: int, B: int, B_pad: int,
                  dtype: int, relu: bool, ldw: Optional[int] = None, ldx: Optional[int] = None,
-                 ldo: Optional[int] = None, bump_seq_ptr: int = 0, name: str = "fwd") -> GemmPlan:
+                 ldo: Optional[int] = None, bump_seq_ptr: int = 0, splits: Optional[int] = None,
+                 name: str = "fwd") -> GemmPlan:
     """out[b, o] = act(x[b, :] . W[o, :] + bias[o]); A = W (K-major, may be peer), B = x (K-major)."""
     assert B_pad % 16 == 0 and B_pad <= 256 and B <= B_pad
     es = elem_size(dtype)
@@ -118,7 +141,10 @@ def forward_plan(*, w_ptr: int, x_ptr: int, out_ptr: int, bias_ptr: int, O: int,
     k = bke(dtype)
     tm_a = N.make_tensor_map(w_ptr, dtype, I, O, ldw * es, k, TILE_M)
     tm_b = N.make_tensor_map(x_ptr, dtype, I, B_pad, ldx * es, k, B_pad)
-    p = _base_params(O, B, I, B_pad, dtype, 1)
+    mtiles = ceil_div(O, TILE_M)
+    splits = auto_splits(I, dtype, mtiles) if splits is None else splits
+    p = _base_params(O, B, I, B_pad, dtype, splits)
+    splits = ceil_div(ceil_div(I, k), p.kc_per_split)  # drop empty trailing splits
     p.epi = N.EPI_TRANSPOSED
     p.out = out_ptr
     p.out_bf16 = int(dtype == N.DT_BF16)
@@ -126,8 +152,10 @@ def forward_plan(*, w_ptr: int, x_ptr: int, out_ptr: int, bias_ptr: int, O: int,
     p.bias = bias_ptr
     p.relu = int(relu)
     p.bump_seq = bump_seq_ptr
-    grid = (ceil_div(O, TILE_M), 1, 1)
-    return GemmPlan(tm_a, tm_b, p, dtype, False, False, 1, grid, name)
+    grid = (mtiles, 1, splits)
+    plan = GemmPlan(tm_a, tm_b, p, dtype, False, False, splits, grid, name)
+    _attach_splitk(plan, mtiles, splits, B_pad)
+    return plan
 
 
 def dw_plan(*, dy_ptr: int, x_ptr: int, O: int, I: int, B_pad: int, dtype: int, push: N.PushTarget,
@@ -163,7 +191,7 @@ def dw_tiles(O: int, I: int, bn: int = 64):
 def dx_plan(*, w_ptr: int, dy_ptr: int, out_ptr: int, mask_ptr: int, O: int, I: int, B: int, B_pad: int,
             dtype: int, ldw: Optional[int] = None, lddy: Optional[int] = None, ldo: Optional[int] = None,
             colsum: Optional[N.PushTarget] = None, colsum_offset: int = 0, colsum_item_base: int = 0,
-            name: str = "dx") -> GemmPlan:
+            splits: Optional[int] = None, name: str = "dx") -> GemmPlan:
     """dx[b, i] = (dy[b, :] . W[:, i]) * (mask[b, i] > 0); A = W (MN-major, may be peer), B = dy (K-major)."""
     assert B_pad % 16 == 0 and B_pad <= 256
     es = elem_size(dtype)
@@ -173,7 +201,10 @@ def dx_plan(*, w_ptr: int, dy_ptr: int, out_ptr: int, mask_ptr: int, O: int, I: 
     ldo = I if ldo is None else ldo
     tm_a = N.make_tensor_map(w_ptr, dtype, I, O, ldw * es, k, k, mn_major=True)
     tm_b = N.make_tensor_map(dy_ptr, dtype, O, B_pad, lddy * es, k, B_pad)
-    p = _base_params(I, B, O, B_pad, dtype, 1)
+    mtiles = ceil_div(I, TILE_M)
+    splits = auto_splits(O, dtype, mtiles) if splits is None else splits
+    p = _base_params(I, B, O, B_pad, dtype, splits)
+    splits = ceil_div(ceil_div(O, k), p.kc_per_split)
     p.epi = N.EPI_TRANSPOSED
     p.out = out_ptr
     p.out_bf16 = int(dtype == N.DT_BF16)
@@ -186,5 +217,7 @@ def dx_plan(*, w_ptr: int, dy_ptr: int, out_ptr: int, mask_ptr: int, O: int, I: 
         p.colsum_offset = colsum_offset
         p.colsum_item_base = colsum_item_base
         p.has_colsum = 1
-    grid = (ceil_div(I, TILE_M), 1, 1)
-    return GemmPlan(tm_a, tm_b, p, dtype, True, False, 1, grid, name)
+    grid = (mtiles, 1, splits)
+    plan = GemmPlan(tm_a, tm_b, p, dtype, True, False, splits, grid, name)
+    _attach_splitk(plan, mtiles, splits, B_pad)
+    return plan

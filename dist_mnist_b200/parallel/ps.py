@@ -159,6 +159,7 @@ class ParameterServer:
         self._P = P
         if self.cfg.backend == "cuda":
             N.check(self.lib.dm_set_device(self.device), "set device")
+            N.ensure_prepared(self.device)  # load every kernel before the persistent one becomes resident
             out = C.c_void_p()
             N.check(self.lib.dm_stream_create(C.byref(out)))
             self._stream = out.value

@@ -299,6 +299,28 @@ class Worker:
         seq_ptr = self.seg.addr("seq")
         self._slots = []
         stream = self.lib.dm_exec_compute_stream(self._exec)
+        # ---- evaluation path (forward + head without gradients; shares the activation buffers) ----
+        self._eval_x = torch.zeros(self.B_pad, self.ld_in, dtype=self.tdtype, device=dev)
+        self._eval_y = torch.zeros(self.B_pad, spec.num_classes, dtype=torch.float32, device=dev)
+        self._eval_res = torch.zeros(4, dtype=torch.int32, device=dev)
+        self._eval_plans = []
+        for l in range(L - 1):
+            wl, bl = lay.by_name[names[l][0]], lay.by_name[names[l][1]]
+            fin, fout = sizes[l]
+            self._eval_plans.append(gemm_ops.forward_plan(
+                w_ptr=self._weight_ptr(wl), x_ptr=self._eval_x.data_ptr() if l == 0 else self.act[l].data_ptr(),
+                out_ptr=self.act[l + 1].data_ptr(), bias_ptr=self.ps_segs[bl.ps].addr("params", bl.offset * 4),
+                O=fout, I=fin, B=self.batch, B_pad=self.B_pad, dtype=self.dt, relu=True, ldw=wl.ld,
+                ldx=self.ld_in if l == 0 else self.act[l].shape[1], ldo=self.act[l + 1].shape[1], name=f"eval_fwd{l}"))
+        wl, bl = lay.by_name[names[L - 1][0]], lay.by_name[names[L - 1][1]]
+        self._eval_plans.append(head_ops.head_plan(
+            h_ptr=self.act[L - 1].data_ptr(), labels_ptr=self._eval_y.data_ptr(),
+            w_last_ptr=self.ps_segs[wl.ps].addr("params", wl.offset * 4),
+            b_last_ptr=self.ps_segs[bl.ps].addr("params", bl.offset * 4), dpre_ptr=self.dact[L - 1].data_ptr(),
+            result_ptr=self._eval_res.data_ptr(), B=self.batch, B_pad=self.B_pad, H=sizes[L - 1][0],
+            num_classes=spec.num_classes, loss_kind=N.LOSS_BOOK if spec.loss == "book" else N.LOSS_XENT,
+            act_bf16=cfg.dtype == "bf16", compute_grads=False, ldh=self.act[L - 1].shape[1]))
+        torch.cuda.synchronize(self.device)
         for slot in range(cfg.pipeline_slots):
             xd, yd, rd, xs, ys = (C.c_void_p() for _ in range(5))
             N.check(self.lib.dm_exec_slot_info(self._exec, slot, C.byref(xd), C.byref(yd), C.byref(rd), C.byref(xs),
@@ -394,6 +416,13 @@ class Worker:
         t = C.c_uint64()
         N.check(self.lib.dm_exec_submit(self._exec, x_ptr or None, y_ptr or None, C.byref(t)), "submit")
         return t.value
+
+    def run_resident(self, n_steps: int, x_base_ptr: int, y_base_ptr: int, x_row_bytes: int, y_row_bytes: int,
+                     n_rows: int, start: int = 0) -> None:
+        """Native loop over a device-resident dataset: step i trains on rows ((start + i) * batch) % n_rows ..
+        (contiguous), copied device-to-device into the slot buffers. Results stay in the executor's history."""
+        N.check(self.lib.dm_exec_run_resident(self._exec, n_steps, x_base_ptr, y_base_ptr, x_row_bytes, y_row_bytes,
+                                              n_rows, self.batch, start), "run resident")
 
     def result(self, ticket: int, wait: bool = True) -> Optional[StepOutput]:
         r = N.StepResult()
@@ -506,17 +535,34 @@ class Worker:
     def evaluate(self, images: torch.Tensor, labels: torch.Tensor) -> Tuple[float, float]:
         """(mean loss, accuracy) of the current PS variables on a host dataset; GPU path uses the hand-written
         accuracy reduction kernel on torch-computed logits of the pulled variables."""
-        params = self.read_variables()
         if self.cfg.backend == "cuda":
-            dev = f"cuda:{self.device}"
-            params = {k: v.to(dev) for k, v in params.items()}
-            images, labels = images.to(dev), labels.to(dev).float().contiguous()
-            logits, _ = mlp.forward_logits(self.spec, params, images.float())
-            logits = logits.contiguous()
-            correct = int(head_ops.accuracy_count(logits, labels).item())
-        else:
-            logits, _ = mlp.forward_logits(self.spec, params, images.float())
-            correct = mlp.accuracy_count(logits, labels)
+            # forward tcgen05 GEMMs (weights pulled from the PS shards) + the head kernel in eval mode; whole
+            # batches only (the step kernels are specialised for this worker's batch size).
+            self.drain()
+            stream = self.compute_stream
+            n_chunks = images.shape[0] // self.batch
+            if n_chunks == 0:
+                raise ValueError(f"evaluate needs at least one full batch of {self.batch} samples")
+            xs = torch.zeros(self.B_pad, self.ld_in, dtype=self.tdtype).pin_memory()
+            ys = torch.zeros(self.B_pad, self.spec.num_classes, dtype=torch.float32).pin_memory()
+            res = torch.zeros(4, dtype=torch.int32).pin_memory()
+            loss_sum, correct = 0.0, 0
+            for c in range(n_chunks):
+                sl = slice(c * self.batch, (c + 1) * self.batch)
+                xs[: self.batch, : images.shape[1]].copy_(images[sl])
+                ys[: self.batch].copy_(labels[sl])
+                N.check(self.lib.dm_memcpy_async(self._eval_x.data_ptr(), xs.data_ptr(), xs.numel() * xs.element_size(), stream))
+                N.check(self.lib.dm_memcpy_async(self._eval_y.data_ptr(), ys.data_ptr(), ys.numel() * 4, stream))
+                for p in self._eval_plans:
+                    p.launch(stream)
+                N.check(self.lib.dm_memcpy_async(res.data_ptr(), self._eval_res.data_ptr(), 16, stream))
+                N.check(self.lib.dm_stream_sync(stream))
+                loss_sum += float(res[:1].view(torch.float32).item())
+                correct += int(res[2].item())
+            return loss_sum / n_chunks, correct / (n_chunks * self.batch)
+        params = self.read_variables()
+        logits, _ = mlp.forward_logits(self.spec, params, images.float())
+        correct = mlp.accuracy_count(logits, labels)
         loss = float(mlp.loss_from_logits(self.spec, logits, labels.float()))
         return loss, correct / max(1, images.shape[0])
 

@@ -1,0 +1,64 @@
+"""Multi-GPU tests (need >= 2 B200s on one box; skipped otherwise): separate OS processes exchange CUDA IPC
+handles through the rendezvous and train over NVLink peer memory."""
+import json
+import os
+import socket
+import subprocess
+import sys
+import time
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SCRIPT = os.path.join(ROOT, "distributed_server-basic.py")
+
+
+def _need_gpus(n):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _spawn(job, idx, ps_hosts, worker_hosts, extra=()):
+    cmd = [sys.executable, SCRIPT, "--job_name", job, "--task_index", str(idx), "--ps_hosts", ps_hosts,
+           "--worker_hosts", worker_hosts, "--backend", "cuda", *extra]
+    env = dict(os.environ, PYTHONPATH=ROOT, PYTHONUNBUFFERED="1")
+    return subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, cwd=ROOT)
+
+
+@pytest.mark.parametrize("extra", [[], ["--optimizer", "sgd", "--push_mode", "atomic", "--learning_rate", "0.05"]])
+def test_cli_one_ps_one_worker_two_gpus(extra):
+    _need_gpus(2)
+    ps_hosts, worker_hosts = f"127.0.0.1:{_free_port()}", f"127.0.0.1:{_free_port()}"
+    common = ["--train_steps", "400", "--learning_rate", "0.001", *extra]
+    ps = _spawn("ps", 0, ps_hosts, worker_hosts, common + ["--ps_exit_when_done"])
+    w0 = _spawn("worker", 0, ps_hosts, worker_hosts, common)
+    out0, _ = w0.communicate(timeout=240)
+    outp, _ = ps.communicate(timeout=60)
+    assert w0.returncode == 0, out0
+    assert ps.returncode == 0, outp
+    logged = [l for l in out0.splitlines() if l.startswith("Train step ")]
+    assert [int(l.split(",")[0].split()[-1]) for l in logged] == [100, 200, 300, 400], out0
+    losses = [float(l.split("loss: ")[1]) for l in logged]
+    assert losses[-1] < losses[0]
+
+
+def test_bench_two_gpus_contract():
+    _need_gpus(2)
+    port = _free_port()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "300",
+           "--warmup", "10"]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["n_gpus"] == 2 and d["value"] > 0 and d["e2e"]["value"] > 0 and d["gpu_launches"] >= 300 * 3
+    assert d["config"]["global_step_after_run"] >= 300
