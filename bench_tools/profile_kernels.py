@@ -37,6 +37,8 @@ def main() -> int:
     ap.add_argument("--time", action="store_true", help="CUDA-event timing of each kernel (not under ncu)")
     ap.add_argument("--graph_time", action="store_true", help="per-kernel time from CUDA-graph replays (warm caches)")
     ap.add_argument("--push", default="mailbox", choices=["mailbox", "local", "atomic"])
+    ap.add_argument("--phases", action="store_true", help="print in-kernel phase timestamps of the GEMM kernels")
+    ap.add_argument("--fwd_splits", type=int, default=None)
     args = ap.parse_args()
     dev = "cuda"
     spec = mlp.get_model(args.model)
@@ -89,7 +91,8 @@ def main() -> int:
                                        out_ptr=act[l + 1].data_ptr(), bias_ptr=params.data_ptr() + bl.offset * 4,
                                        O=fout, I=fin, B=B, B_pad=B_pad, dtype=dt, relu=True, ldw=wl.ld,
                                        ldx=ld_in if l == 0 else act[l].shape[1], ldo=act[l + 1].shape[1],
-                                       bump_seq_ptr=seq.data_ptr() if l == 0 else 0, name=f"fwd{l}"))
+                                       bump_seq_ptr=seq.data_ptr() if l == 0 else 0, splits=args.fwd_splits,
+                                       name=f"fwd{l}"))
     wl, bl = lay.by_name[names[L - 1][0]], lay.by_name[names[L - 1][1]]
     hb = lay.by_name[names[L - 2][1]]
     plans.append(head.head_plan(h_ptr=act[L - 1].data_ptr(), labels_ptr=y.data_ptr(),
@@ -144,6 +147,52 @@ def main() -> int:
     P.global_step, P.host_stop, P.exit_counter = ctrl.data_ptr(), ctrl.data_ptr() + 4, ctrl.data_ptr() + 8
     P.worker_done, P.inbox_table = ctrl.data_ptr() + 64, table.data_ptr()
     done_view = ctrl[16:17]
+
+    if args.phases:
+        ts = torch.zeros(16 + 2 * 120, dtype=torch.int64, device=dev)
+        names_ph = ["entry", "prologue done", "1st stage TMA issued", "1st full barrier", "last MMA committed",
+                    "tmem_full seen", "-", "epilogue done", "exit"]
+        for p_ in plans:
+            if not hasattr(p_, "tm_a"):
+                continue
+            p_.params.debug_ts = ts.data_ptr()
+            for _ in range(3):
+                p_.launch(N.current_stream_ptr())
+            torch.cuda.synchronize()
+            t = ts.tolist()
+            print(f"{p_.name}: grid={p_.grid} stages={p_.params.stages} " + "  ".join(
+                f"{names_ph[i]}=+{t[i] - t[0]}" for i in (1, 2, 3, 4, 5, 7, 8)) + " (SM cycles)")
+            ncta = min(120, p_.grid[0] * p_.grid[1] * p_.grid[2])
+            ent = [t[16 + 2 * i] for i in range(ncta)]
+            ext = [t[17 + 2 * i] for i in range(ncta)]
+            base = min(ent)
+            print("    per-CTA wall clock (ns since first entry): entry " + " ".join(str(e - base) for e in ent))
+            print("                                               exit  " + " ".join(str(e - base) for e in ext))
+            # two launches back to back: gap between the first kernel's last exit and the second kernel's first entry
+            ts.zero_()
+            p_.launch(N.current_stream_ptr())
+            torch.cuda.synchronize()
+            first_exit = max(ts.tolist()[17 + 2 * i] for i in range(ncta))
+            ts.zero_()
+            g = torch.cuda.CUDAGraph()
+            s_ = torch.cuda.Stream()
+            with torch.cuda.stream(s_):
+                p_.launch(s_.cuda_stream)
+                s_.synchronize()
+                with torch.cuda.graph(g, stream=s_):
+                    p_.launch(s_.cuda_stream)
+                    p_.launch(s_.cuda_stream)
+                    p_.launch(s_.cuda_stream)
+                ts.zero_()
+                s_.synchronize()
+                g.replay()
+                s_.synchronize()
+            t2 = ts.tolist()
+            ent = [t2[16 + 2 * i] for i in range(ncta)]
+            ext = [t2[17 + 2 * i] for i in range(ncta)]
+            print(f"    graph of 3 launches, last launch: first entry..last exit = {max(ext) - min(ent)} ns")
+            p_.params.debug_ts = None
+        return 0
 
     if args.graph_time:
         # warm-cache per-kernel time: R back-to-back launches of one plan inside a CUDA graph (no host launch

@@ -53,10 +53,11 @@ class GemmParams(C.Structure):
         ("colsum_item_base", C.c_int), ("has_colsum", C.c_int),
         ("push", PushTarget),
         ("push_offset", C.c_uint64),
-        ("push_item_base", C.c_int), ("pad_", C.c_int),
+        ("push_item_base", C.c_int), ("push_staged", C.c_int),
         ("bump_seq", C.c_void_p),
         ("splitk_scratch", C.c_void_p),
         ("splitk_counter", C.c_void_p),
+        ("debug_ts", C.c_void_p),
     ]
 
 

@@ -147,18 +147,19 @@ int dm_exec_create(int device, int nslots, size_t x_bytes, size_t y_bytes, void*
   EX_CUDA(cudaStreamCreateWithFlags(&ex->copy, cudaStreamNonBlocking));
   ex->slots.resize(nslots);
   for (auto& s : ex->slots) {
-    EX_CUDA(cudaMalloc(&s.x_dev, x_bytes));
-    EX_CUDA(cudaMalloc(&s.y_dev, y_bytes));
-    EX_CUDA(cudaMemset(s.x_dev, 0, x_bytes));
-    EX_CUDA(cudaMemset(s.y_dev, 0, y_bytes));
+    // x and y of a slot are one allocation (device and pinned staging alike): the native loop then moves a
+    // whole batch host->device with a single cudaMemcpyAsync.
+    const size_t x_al = (x_bytes + 255) & ~size_t(255);
+    EX_CUDA(cudaMalloc(&s.x_dev, x_al + y_bytes));
+    EX_CUDA(cudaMemset(s.x_dev, 0, x_al + y_bytes));
+    s.y_dev = static_cast<uint8_t*>(s.x_dev) + x_al;
     EX_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.res_dev), sizeof(dm::StepResult)));
     EX_CUDA(cudaMemset(s.res_dev, 0, sizeof(dm::StepResult)));
     EX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&s.res_host), sizeof(dm::StepResult), cudaHostAllocDefault));
-    EX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&s.x_stage), x_bytes, cudaHostAllocDefault));
-    EX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&s.y_stage), y_bytes, cudaHostAllocDefault));
+    EX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&s.x_stage), x_al + y_bytes, cudaHostAllocDefault));
+    s.y_stage = s.x_stage + x_al;
     memset(s.res_host, 0, sizeof(dm::StepResult));
-    memset(s.x_stage, 0, x_bytes);
-    memset(s.y_stage, 0, y_bytes);
+    memset(s.x_stage, 0, x_al + y_bytes);
     EX_CUDA(cudaEventCreateWithFlags(&s.in_ready, cudaEventDisableTiming));
     EX_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
   }
@@ -217,8 +218,13 @@ int dm_exec_submit(void* h, const void* x_src, const void* y_src, uint64_t* tick
   ExecSlot& s = ex->slots[(t - 1) % ex->slots.size()];
   if (ex->retire(s) != 0) return -1;
   if (x_src != nullptr) {
-    EX_CUDA(cudaMemcpyAsync(s.x_dev, x_src, ex->x_bytes, cudaMemcpyDefault, ex->copy));
-    EX_CUDA(cudaMemcpyAsync(s.y_dev, y_src, ex->y_bytes, cudaMemcpyDefault, ex->copy));
+    if (x_src == s.x_stage && y_src == s.y_stage) {
+      const size_t x_al = (ex->x_bytes + 255) & ~size_t(255);
+      EX_CUDA(cudaMemcpyAsync(s.x_dev, s.x_stage, x_al + ex->y_bytes, cudaMemcpyHostToDevice, ex->copy));
+    } else {
+      EX_CUDA(cudaMemcpyAsync(s.x_dev, x_src, ex->x_bytes, cudaMemcpyDefault, ex->copy));
+      EX_CUDA(cudaMemcpyAsync(s.y_dev, y_src, ex->y_bytes, cudaMemcpyDefault, ex->copy));
+    }
     EX_CUDA(cudaEventRecord(s.in_ready, ex->copy));
     EX_CUDA(cudaStreamWaitEvent(ex->compute, s.in_ready, 0));
   }
@@ -320,11 +326,9 @@ int dm_exec_destroy(void* h) {
     if (s.exec) cudaGraphExecDestroy(s.exec);
     if (s.graph) cudaGraphDestroy(s.graph);
     cudaFree(s.x_dev);
-    cudaFree(s.y_dev);
     cudaFree(s.res_dev);
     cudaFreeHost(s.res_host);
     cudaFreeHost(s.x_stage);
-    cudaFreeHost(s.y_stage);
     cudaEventDestroy(s.in_ready);
     cudaEventDestroy(s.done);
   }

@@ -86,13 +86,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int stage_bytes = kABytes + b_bytes;
   const int stages = p.stages;
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  // the operand ring doubles as the push epilogue's transpose tile (128 x (bn + 4) fp32); keep in sync with
+  // gemm_smem_bytes()
+  int ring_bytes = stages * stage_bytes;
+  const int tile_bytes = (kTileM * (bn + 4) * 4 + 1023) & ~1023;
+  if (ring_bytes < tile_bytes) ring_bytes = tile_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + ring_bytes);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full_bar = empty_bar + stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // optional phase timestamps (SM cycle counter) of CTA (0,0,0) — bench_tools/profile_kernels.py --phases
+  long long* dbg = (p.debug_ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.debug_ts : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+  // every CTA: wall-clock (globaltimer, ns) entry/exit stamps, to see stragglers and launch skew
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (p.debug_ts != nullptr && threadIdx.x == 0 && cta_lin < 120) p.debug_ts[16 + 2 * cta_lin] = static_cast<long long>(globaltimer_ns());
   const int m0 = blockIdx.x * kTileM;
   const int n0 = blockIdx.y * bn;
   const int kc_total = (p.K + BKE - 1) / BKE;
@@ -125,6 +136,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   if (warp == 0) {
@@ -151,6 +163,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int slab = 0; slab < bn / SLAB; ++slab)
             tma_load_2d(sb + slab * (BKE * 128), &tmB, &full_bar[s], n0 + slab * SLAB, k0);
         }
+        if (dbg && i == 0) dbg[2] = clock64();
       }
     }
   } else if (warp == 1) {
@@ -161,6 +174,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t ph = (i / stages) & 1;
       mbar_wait(&full_bar[s], ph);
       tcgen05_fence_after();
+      if (dbg && lane == 0 && i == 0) dbg[3] = clock64();
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
         const uint32_t b_addr = a_addr + kABytes;
@@ -175,14 +189,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           MmaKind<T>::mma(tmem_base, adesc, bdesc, idesc, (i > 0 || j > 0) ? 1u : 0u);
         }
         tcgen05_commit(&empty_bar[s]);
-        if (i == nkc - 1) tcgen05_commit(tmem_full_bar);
+        if (i == nkc - 1) { tcgen05_commit(tmem_full_bar); if (dbg) dbg[4] = clock64(); }
       }
       __syncwarp();
     }
   } else {
     // ===================== epilogue warps (TMEM -> registers -> global / peer) =====================
+    // the bias (a peer load from the PS shard) is requested before the accumulator wait so that its NVLink
+    // round trip overlaps the K loop
+    const int m_pref = m0 + (warp & 3) * 32 + lane;
+    const float bias_pref = (p.epi == EPI_TRANSPOSED && p.bias != nullptr && m_pref < p.M) ? p.bias[m_pref] : 0.f;
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
+    if (dbg && threadIdx.x == 64) dbg[5] = clock64();
     const int q = warp & 3;
     const int m = m0 + q * 32 + lane;
     const bool m_ok = m < p.M;
@@ -196,13 +215,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       bool finalize = true;
       float* part_base = nullptr;
       if (nsplit > 1) {
-        part_base = p.splitk_scratch + (static_cast<size_t>(blockIdx.x) * nsplit * kTileM + q * 32 + lane) * bn;
-        float* mine = part_base + static_cast<size_t>(blockIdx.z) * kTileM * bn;
+        // scratch layout [mtile][split][n][128] with the tile row (= lane) fastest: every warp store / load below
+        // is one fully used 128-byte line (the row-per-thread layout cost 32 line transactions per instruction
+        // and made the fix-up take 8 us).
+        part_base = p.splitk_scratch + static_cast<size_t>(blockIdx.x) * nsplit * bn * kTileM + q * 32 + lane;
+        float* mine = part_base + static_cast<size_t>(blockIdx.z) * bn * kTileM;
         for (int c0 = 0; c0 < bn; c0 += 16) {
           float v[16];
           tmem_ld_32x32b_x16(taddr + c0, v);
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) st_global_v4f32(mine + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 16; ++j) mine[static_cast<size_t>(c0 + j) * kTileM] = v[j];
         }
         __threadfence();
         named_bar_sync(1, 128);
@@ -212,7 +234,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (finalize) __threadfence();
       }
       if (finalize) {
-        const float bias = (p.bias != nullptr && m_ok) ? p.bias[m] : 0.f;
+        const float bias = bias_pref;
         float colsum = 0.f;
         for (int c0 = 0; c0 < bn; c0 += 16) {
           float v[16];
@@ -221,12 +243,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = 0.f;
-            for (int z = 0; z < nsplit; ++z) {
-              const float4* src = reinterpret_cast<const float4*>(part_base + static_cast<size_t>(z) * kTileM * bn + c0);
+            // 8 partial tiles (32 independent 16-byte L2 loads) in flight per round: the fix-up is a latency
+            // chain of ceil(nsplit / 8) L2 round trips instead of nsplit.
+            for (int z0 = 0; z0 < nsplit; z0 += 8) {
+              float t[8][16];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 t = __ldcg(src + j);
-                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+              for (int zz = 0; zz < 8; ++zz) {
+                const int z = min(z0 + zz, nsplit - 1);
+                const float* src = part_base + (static_cast<size_t>(z) * bn + c0) * kTileM;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) t[zz][j] = __ldcg(src + static_cast<size_t>(j) * kTileM);
+              }
+#pragma unroll
+              for (int zz = 0; zz < 8; ++zz) {
+                if (z0 + zz < nsplit) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] += t[zz][j];
+                }
               }
             }
           }
@@ -254,34 +287,74 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         epilogue_colsum(p, colsum, m, m_ok);
       }
     } else {
-      // EPI_ROWMAJOR_PUSH: lane m owns row m of dW; push bn consecutive columns starting at n0.
+      // EPI_ROWMAJOR_PUSH: the gradient push. TMEM lane m holds row m of the dW tile; pushing straight from
+      // registers would make every 16-byte store of a warp hit a different row (32 partial lines per
+      // instruction, and 16-byte packets on NVLink). The tile is therefore transposed through shared memory
+      // (the operand stages are free once the accumulator is complete) so that each warp instruction writes
+      // whole 256-byte row segments: lanes 0..15 one row, lanes 16..31 the next.
       const ResolvedPush r = resolve_push(p.push);
-      float* row = r.base + p.push_offset + static_cast<size_t>(m) * p.ldo + n0;
-      const bool vec_ok = ((p.ldo & 3) == 0) && ((p.push_offset & 3) == 0);
-      for (int c0 = 0; c0 < bn; c0 += 16) {
-        float v[16];
-        tmem_ld_32x32b_x16(taddr + c0, v);
-        if (!m_ok) continue;
-        const int n = n0 + c0;
-        if (p.push.mode == PUSH_ATOMIC) {
-          const float sc = p.push.scale;
-          if (vec_ok && n + 16 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              red_add_sys_v4f32(row + c0 + j, sc * v[j], sc * v[j + 1], sc * v[j + 2], sc * v[j + 3]);
+      float* gbase = r.base + p.push_offset;
+      const bool vec_ok = ((p.ldo & 3) == 0) && ((p.push_offset & 3) == 0) && ((p.N & 3) == 0);
+      if (p.push_staged) {
+        const int ldc = bn + 4;                                   // padded row stride (floats) of the staging tile
+        float* sC = reinterpret_cast<float*>(smem) + static_cast<size_t>(q * 32) * ldc;   // this warp's 32 rows
+        for (int c0 = 0; c0 < bn; c0 += 16) {
+          float v[16];
+          tmem_ld_32x32b_x16(taddr + c0, v);
+          float4* dst = reinterpret_cast<float4*>(sC + lane * ldc + c0);
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        __syncwarp();
+        const int vec_per_row = bn >> 2;
+        const float sc = p.push.scale;
+        for (int idx = lane; idx < 32 * vec_per_row; idx += 32) {
+          const int rl = idx / vec_per_row;
+          const int c4 = (idx - rl * vec_per_row) << 2;
+          const int mm = m0 + q * 32 + rl;
+          const int n = n0 + c4;
+          if (mm >= p.M || n >= p.N) continue;
+          const float4 t = *reinterpret_cast<const float4*>(sC + rl * ldc + c4);
+          float* dstp = gbase + static_cast<size_t>(mm) * p.ldo + n;
+          if (vec_ok) {
+            if (p.push.mode == PUSH_ATOMIC) red_add_sys_v4f32(dstp, sc * t.x, sc * t.y, sc * t.z, sc * t.w);
+            else st_global_v4f32(dstp, t.x, t.y, t.z, t.w);
           } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n + j < p.N) red_add_sys_f32(row + c0 + j, sc * v[j]);
+            const float tv[4] = {t.x, t.y, t.z, t.w};
+  #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (n + j < p.N) {
+                if (p.push.mode == PUSH_ATOMIC) red_add_sys_f32(dstp + j, sc * tv[j]);
+                else dstp[j] = tv[j];
+              }
+            }
           }
-        } else {
+        }
+      } else {
+        // direct variant: lane m pushes its own row run from registers (16-byte stores, one row per lane)
+        float* row = gbase + static_cast<size_t>(m) * p.ldo + n0;
+        const float sc = p.push.scale;
+        for (int c0 = 0; c0 < bn; c0 += 16) {
+          float v[16];
+          tmem_ld_32x32b_x16(taddr + c0, v);
+          if (!m_ok) continue;
+          const int n = n0 + c0;
           if (vec_ok && n + 16 <= p.N) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) st_global_v4f32(row + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 16; j += 4) {
+              if (p.push.mode == PUSH_ATOMIC)
+                red_add_sys_v4f32(row + c0 + j, sc * v[j], sc * v[j + 1], sc * v[j + 2], sc * v[j + 3]);
+              else
+                st_global_v4f32(row + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n + j < p.N) row[c0 + j] = v[j];
+            for (int j = 0; j < 16; ++j) {
+              if (n + j < p.N) {
+                if (p.push.mode == PUSH_ATOMIC) red_add_sys_f32(row + c0 + j, sc * v[j]);
+                else row[c0 + j] = v[j];
+              }
+            }
           }
         }
       }
@@ -296,17 +369,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   }
 
+  if (dbg && threadIdx.x == 64) dbg[7] = clock64();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+  if (dbg && threadIdx.x == 0) dbg[8] = clock64();
+  if (p.debug_ts != nullptr && threadIdx.x == 0 && cta_lin < 120) p.debug_ts[17 + 2 * cta_lin] = static_cast<long long>(globaltimer_ns());
 }
 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 size_t gemm_smem_bytes(int bn, int stages) {
-  return static_cast<size_t>(stages) * (kABytes + bn * 128) + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+  size_t ring = static_cast<size_t>(stages) * (kABytes + bn * 128);
+  const size_t stage_tile = static_cast<size_t>(kTileM) * (bn + 4) * sizeof(float);  // push-epilogue transpose tile
+  if (ring < stage_tile) ring = (stage_tile + 1023) & ~size_t(1023);
+  return ring + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
 }
 
 constexpr int kMaxDynSmem = 226 * 1024;  // 227 KB per-block limit minus the kernel's static shared memory

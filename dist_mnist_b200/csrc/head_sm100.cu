@@ -141,85 +141,85 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
   __syncthreads();
   const uint32_t seq = s_seq;
 
-  // ---- phase B: logits. thread -> (row b, class c); 16 lanes share a row (broadcast loads of h) ----
-  {
-    const int c = tid & (kMaxC - 1);
-    const float bias = c < C ? p.b_last[c] : 0.f;
-    const float* wrow = sW + c * ldw;
-    const int H4 = ((p.ldh & 3) == 0) ? (H & ~3) : 0;
-    for (int b = tid / kMaxC; b < B; b += kHeadThreads / kMaxC) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      const size_t rowoff = static_cast<size_t>(b) * p.ldh;
-#pragma unroll 4
-      for (int k = 0; k < H4; k += 4) {
-        const float4 hv = ld_act4(p.h, rowoff + k, p.act_bf16);
-        const float4 wv = *reinterpret_cast<const float4*>(wrow + k);
-        a0 = fmaf(hv.x, wv.x, a0); a1 = fmaf(hv.y, wv.y, a1);
-        a2 = fmaf(hv.z, wv.z, a2); a3 = fmaf(hv.w, wv.w, a3);
-      }
-      for (int k = H4; k < H; ++k) a0 = fmaf(ld_act(p.h, rowoff + k, p.act_bf16), wrow[k], a0);
-      sLogit[b * kMaxC + c] = (a0 + a1) + (a2 + a3) + bias;
-    }
-  }
-  __syncthreads();
-
-  // ---- phase C: softmax / loss / accuracy / dlogits, one thread per row ----
+  // ---- phase B+C: logits, softmax, loss, accuracy and dlogits. thread -> (row b, class c): the 16 lanes of a
+  //      half-warp own one batch row, so every per-row reduction is four xor-shuffles and the logits never
+  //      leave registers. ----
   float loss_part = 0.f;
   float corr_part = 0.f;
-  for (int b = tid; b < B; b += kHeadThreads) {
-    float z[kMaxC], y[kMaxC];
-    float zmax = -INFINITY, ysum = 0.f;
-    int zarg = 0, yarg = 0;
-    float ybest = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < kMaxC; ++c) {
-      if (c < C) {
-        z[c] = sLogit[b * kMaxC + c];
-        y[c] = p.labels[static_cast<size_t>(b) * C + c];
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < kMaxC; ++c) {
-      if (c < C) {
-        if (z[c] > zmax) { zmax = z[c]; zarg = c; }
-        if (y[c] > ybest) { ybest = y[c]; yarg = c; }
-        ysum += y[c];
-      }
-    }
-    float esum = 0.f;
-    float e[kMaxC];
-#pragma unroll
-    for (int c = 0; c < kMaxC; ++c)
-      if (c < C) { e[c] = __expf(z[c] - zmax); esum += e[c]; }
-    const float inv = 1.f / esum;
-    corr_part += (zarg == yarg) ? 1.f : 0.f;
-    if (p.loss_kind == LOSS_BOOK) {
-      // L = -(1/(B*C)) sum y*log(clip(p,1e-10,1));  dL/dp = -y/(B*C*p) where the clip passes gradient
-      const float k = 1.f / (static_cast<float>(B) * static_cast<float>(C));
-      float g[kMaxC];
-      float gp = 0.f;
-#pragma unroll
-      for (int c = 0; c < kMaxC; ++c) {
-        if (c < C) {
-          const float pc = e[c] * inv;
-          const float pcl = fminf(fmaxf(pc, 1e-10f), 1.0f);
-          loss_part -= k * y[c] * __logf(pcl);
-          const bool pass = (pc >= 1e-10f) && (pc <= 1.0f);
-          g[c] = pass ? (-k * y[c] / pc) : 0.f;
-          gp += g[c] * pc;
+  {
+    const int c = lane & (kMaxC - 1);
+    const bool c_ok = c < C;
+    const float bias = c_ok ? p.b_last[c] : 0.f;
+    const float* wrow = sW + c * ldw;
+    const bool h_smem = gridDim.x == 1;          // the staged slice is the whole of h
+    const int H4 = (h_smem || (p.ldh & 3) == 0) ? (H & ~3) : 0;
+    for (int b0 = warp * 2; b0 < B; b0 += (kHeadThreads / 32) * 2) {   // warp-uniform trip count
+      const int b = b0 + (lane >> 4);
+      const bool row_ok = b < B;
+      const int bs = row_ok ? b : B - 1;
+      const float y = (c_ok && row_ok) ? p.labels[static_cast<size_t>(bs) * C + c] : 0.f;  // in flight during the dot
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      if (h_smem) {
+        const float* hrow = sHs + bs * kHeadSlice;
+#pragma unroll 4
+        for (int k = 0; k < H4; k += 4) {
+          const float4 hv = *reinterpret_cast<const float4*>(hrow + k);
+          const float4 wv = *reinterpret_cast<const float4*>(wrow + k);
+          a0 = fmaf(hv.x, wv.x, a0); a1 = fmaf(hv.y, wv.y, a1);
+          a2 = fmaf(hv.z, wv.z, a2); a3 = fmaf(hv.w, wv.w, a3);
         }
+        for (int k = H4; k < H; ++k) a0 = fmaf(hrow[k], wrow[k], a0);
+      } else {
+        const size_t rowoff = static_cast<size_t>(bs) * p.ldh;
+#pragma unroll 8
+        for (int k = 0; k < H4; k += 4) {
+          const float4 hv = ld_act4(p.h, rowoff + k, p.act_bf16);
+          const float4 wv = *reinterpret_cast<const float4*>(wrow + k);
+          a0 = fmaf(hv.x, wv.x, a0); a1 = fmaf(hv.y, wv.y, a1);
+          a2 = fmaf(hv.z, wv.z, a2); a3 = fmaf(hv.w, wv.w, a3);
+        }
+        for (int k = H4; k < H; ++k) a0 = fmaf(ld_act(p.h, rowoff + k, p.act_bf16), wrow[k], a0);
       }
+      const float z = c_ok ? (a0 + a1) + (a2 + a3) + bias : -INFINITY;
+      // row reductions over the 16-lane group
+      float zmax = z, ybest = c_ok ? y : -INFINITY, ysum = y;
 #pragma unroll
-      for (int c = 0; c < kMaxC; ++c)
-        sLogit[b * kMaxC + c] = c < C ? (e[c] * inv) * (g[c] - gp) : 0.f;
-    } else {
-      // L = (1/B) sum_b -sum_c y*log_softmax(z);  dz = (p*sum(y) - y)/B
-      const float k = 1.f / static_cast<float>(B);
-      const float lse = zmax + __logf(esum);
+      for (int o = 8; o > 0; o >>= 1) {
+        zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+        ybest = fmaxf(ybest, __shfl_xor_sync(0xffffffffu, ybest, o));
+        ysum += __shfl_xor_sync(0xffffffffu, ysum, o);
+      }
+      int zarg = (c_ok && z == zmax) ? c : kMaxC, yarg = (c_ok && y == ybest) ? c : kMaxC;  // first maximum wins
+      const float e = c_ok ? __expf(z - zmax) : 0.f;
+      float esum = e;
 #pragma unroll
-      for (int c = 0; c < kMaxC; ++c) {
-        if (c < C) loss_part -= k * y[c] * (z[c] - lse);
-        sLogit[b * kMaxC + c] = c < C ? k * (e[c] * inv * ysum - y[c]) : 0.f;
+      for (int o = 8; o > 0; o >>= 1) {
+        zarg = min(zarg, __shfl_xor_sync(0xffffffffu, zarg, o));
+        yarg = min(yarg, __shfl_xor_sync(0xffffffffu, yarg, o));
+        esum += __shfl_xor_sync(0xffffffffu, esum, o);
+      }
+      const float pc = e / esum;
+      float dl = 0.f, lc = 0.f;
+      if (p.loss_kind == LOSS_BOOK) {
+        // L = -(1/(B*C)) sum y*log(clip(p,1e-10,1));  dL/dp = -y/(B*C*p) where the clip passes gradient
+        const float k = 1.f / (static_cast<float>(B) * static_cast<float>(C));
+        const bool pass = c_ok && (pc >= 1e-10f) && (pc <= 1.0f);
+        const float g = pass ? (-k * y / pc) : 0.f;
+        float gp = g * pc;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) gp += __shfl_xor_sync(0xffffffffu, gp, o);
+        dl = pc * (g - gp);
+        lc = c_ok ? -k * y * __logf(fminf(fmaxf(pc, 1e-10f), 1.0f)) : 0.f;
+      } else {
+        // L = (1/B) sum_b -sum_c y*log_softmax(z);  dz = (p*sum(y) - y)/B
+        const float k = 1.f / static_cast<float>(B);
+        dl = k * (pc * ysum - y);
+        lc = c_ok ? -k * y * (z - (zmax + __logf(esum))) : 0.f;
+      }
+      if (row_ok) {
+        sLogit[b * kMaxC + c] = c_ok ? dl : 0.f;
+        loss_part += lc;
+        if (c == 0) corr_part += (zarg == yarg) ? 1.f : 0.f;
       }
     }
   }

@@ -65,10 +65,11 @@ struct GemmParams {
   PushTarget push;      // EPI_ROWMAJOR_PUSH destination
   uint64_t push_offset; // element offset of the variable inside push.base
   int push_item_base;   // first flag item index for this variable's tiles (tile = mtile * ntiles + ntile)
-  int pad_;
+  int push_staged;      // 1: transpose the dW tile through smem so each warp store covers whole 256-byte row runs
   uint32_t* bump_seq;   // if set, CTA (0,0,0) increments it: the first kernel of a step opens a new push seq
   float* splitk_scratch;     // gridDim.z > 1: [mtiles][splits][128][bn] fp32 partial tiles
   uint32_t* splitk_counter;  // gridDim.z > 1: [mtiles] arrival counters (self-resetting)
+  long long* debug_ts;       // optional: 9 clock64() phase stamps of CTA (0,0,0); null in production
 };
 
 // Softmax-cross-entropy head (last dense layer + loss + its gradients), see head_sm100.cu

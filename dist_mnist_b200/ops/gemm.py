@@ -14,6 +14,7 @@ Reference parity: MatMul / BiasAdd / Relu and their gradients at
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -96,11 +97,12 @@ def _pick_stages(bn: int, kc: int) -> int:
 
 
 def auto_splits(K: int, dtype: int, mtiles: int) -> int:
-    """Split-K factor for the K-loop GEMMs (forward, dX). One SM's TMA front-end moves 128-byte-wide boxes at
-    only ~16 B/clk, so a long K loop is spread over several CTAs (<= 2 k-chunks each) whose partial tiles are
-    summed by the last-arriving CTA. Bounded so that the grid stays well inside one wave of 148 SMs."""
+    """Split-K factor for the K-loop GEMMs (forward, dX). Measured on B200 (profiles/gemm_phase_timestamps_*):
+    one CTA streams a 20 KB k-chunk (128-byte-wide TMA boxes) every ~730 cycles, so a 25-chunk K loop costs
+    ~9 us on one SM. The loop is therefore spread over up to 8 CTAs (~3-4 k-chunks each) whose fp32 partial
+    tiles are summed by the last-arriving CTA in a single round of independent L2 loads."""
     kc = ceil_div(K, bke(dtype))
-    return max(1, min(16, ceil_div(kc, 2), max(1, 96 // max(1, mtiles))))
+    return max(1, min(8, ceil_div(kc, 3), max(1, 96 // max(1, mtiles))))
 
 
 def _attach_splitk(plan: "GemmPlan", mtiles: int, splits: int, bn: int) -> None:
@@ -175,6 +177,7 @@ def dw_plan(*, dy_ptr: int, x_ptr: int, O: int, I: int, B_pad: int, dtype: int, 
     p.push = push
     p.push_offset = push_offset
     p.push_item_base = item_base
+    p.push_staged = int(os.environ.get("DM_PUSH_STAGED", "0") == "1")
     grid = (ceil_div(O, TILE_M), ceil_div(I, bn), 1)
     return GemmPlan(tm_a, tm_b, p, dtype, True, True, 1, grid, name)
 
