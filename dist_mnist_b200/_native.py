@@ -37,6 +37,8 @@ class PushTarget(C.Structure):
         ("flags", C.c_void_p),
         ("flag_slot_stride", C.c_uint32),
         ("nslots", C.c_uint32),
+        ("gpu_scope", C.c_uint32),
+        ("pad_", C.c_uint32),
         ("seq_ptr", C.c_void_p),
     ]
 
@@ -99,6 +101,7 @@ class PsServeParams(C.Structure):
         ("global_step", C.c_void_p), ("worker_done", C.c_void_p), ("host_stop", C.c_void_p),
         ("inbox_table", C.c_void_p),
         ("exit_counter", C.c_void_p),
+        ("gpu_scope", C.c_uint32), ("pad_", C.c_uint32),
     ]
 
 

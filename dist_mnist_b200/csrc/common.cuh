@@ -208,6 +208,22 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Scope-selectable variants: when every party of a flag protocol runs on the *same* GPU (ps and worker sharing
+// a device), gpu scope is sufficient and several times cheaper than the system-scope fence NVLink peers need.
+__device__ __forceinline__ void st_release_scoped_u32(uint32_t* p, uint32_t v, uint32_t gpu_scope) {
+  if (gpu_scope) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+  else st_release_sys_u32(p, v);
+}
+__device__ __forceinline__ uint32_t ld_acquire_scoped_u32(const uint32_t* p, uint32_t gpu_scope) {
+  uint32_t v;
+  if (gpu_scope) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  else v = ld_acquire_sys_u32(p);
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_scoped(uint32_t gpu_scope) {
+  if (gpu_scope) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  else fence_acq_rel_sys();
+}
 __device__ __forceinline__ uint32_t ld_relaxed_sys_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

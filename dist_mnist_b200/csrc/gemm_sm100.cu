@@ -59,7 +59,7 @@ __device__ __forceinline__ void epilogue_colsum(const GemmParams& p, float colsu
   }
   if (p.colsum.mode == PUSH_MAILBOX) {
     named_bar_sync(1, 128);  // orders every lane's P2P store before the one cumulative st.release.sys below
-    if (threadIdx.x == 64) st_release_sys_u32(r.flags + p.colsum_item_base + blockIdx.x, r.seq);
+    if (threadIdx.x == 64) st_release_scoped_u32(r.flags + p.colsum_item_base + blockIdx.x, r.seq, p.colsum.gpu_scope);
   }
 }
 
@@ -228,10 +228,59 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         __threadfence();
         named_bar_sync(1, 128);
-        if (threadIdx.x == 64) s_last = (atomicAdd(p.splitk_counter + blockIdx.x, 1u) == static_cast<uint32_t>(nsplit - 1));
-        named_bar_sync(1, 128);
-        finalize = s_last != 0;
-        if (finalize) __threadfence();
+        if (!p.has_colsum) {
+          // ---- distributed fix-up (forward GEMMs): wait until all splits of this tile have parked their
+          // partials (the grid is far smaller than one wave, so all CTAs are co-resident), then every CTA
+          // finishes its own slice of the tile's columns: bn/nsplit columns x nsplit partials per lane, all
+          // loads independent and coalesced — instead of one CTA re-reading every partial tile.
+          if (threadIdx.x == 64) {
+            uint32_t* ctr = p.splitk_counter + blockIdx.x;      // monotonic: nsplit arrivals per launch
+            const uint32_t old = atomicAdd(ctr, 1u);
+            const uint32_t target = (old / nsplit + 1u) * nsplit;
+            const uint64_t t0 = globaltimer_ns();
+            while (static_cast<int32_t>(ld_acquire_scoped_u32(ctr, 1u) - target) < 0) {
+              if (globaltimer_ns() - t0 > DM_SPIN_TIMEOUT_NS) {
+                printf("[dm] split-K barrier timeout tile=%d split=%d\n", blockIdx.x, blockIdx.z);
+                __trap();
+              }
+            }
+          }
+          named_bar_sync(1, 128);
+          const int cw = (bn + nsplit - 1) / nsplit;
+          const int c_begin = blockIdx.z * cw;
+          const int c_end = min(bn, c_begin + cw);
+          const float* col0 = part_base;  // + (z * bn + c) * kTileM
+          for (int c = c_begin; c < c_end; ++c) {
+            float acc = 0.f;
+#pragma unroll 8
+            for (int z = 0; z < nsplit; ++z) acc += __ldcg(col0 + (static_cast<size_t>(z) * bn + c) * kTileM);
+            const int n = n0 + c;
+            if (n < p.N && m_ok) {
+              float val = acc + bias_pref;
+              if (p.relu) val = fmaxf(val, 0.f);
+              if (p.mask != nullptr) {
+                const float a = p.mask_bf16
+                                    ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(
+                                          p.mask)[static_cast<size_t>(n) * p.ldmask + m])
+                                    : reinterpret_cast<const float*>(p.mask)[static_cast<size_t>(n) * p.ldmask + m];
+                val = a > 0.f ? val : 0.f;
+              }
+              const size_t o = static_cast<size_t>(n) * p.ldo + m;
+              if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(val);
+              else reinterpret_cast<float*>(p.out)[o] = val;
+            }
+          }
+          finalize = false;
+        } else {
+          // ---- last-arriver fix-up (dX GEMMs, whose bias-gradient column sums need the whole tile) ----
+          if (threadIdx.x == 64) {
+            const uint32_t old = atomicAdd(p.splitk_counter + blockIdx.x, 1u);
+            s_last = ((old + 1u) % static_cast<uint32_t>(nsplit)) == 0u;
+          }
+          named_bar_sync(1, 128);
+          finalize = s_last != 0;
+          if (finalize) __threadfence();
+        }
       }
       if (finalize) {
         const float bias = bias_pref;
@@ -283,8 +332,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
-        if (nsplit > 1 && threadIdx.x == 64) p.splitk_counter[blockIdx.x] = 0;  // ready for the next launch
-        epilogue_colsum(p, colsum, m, m_ok);
+        epilogue_colsum(p, colsum, m, m_ok);  // (the arrival counter is monotonic: no reset needed)
       }
     } else {
       // EPI_ROWMAJOR_PUSH: the gradient push. TMEM lane m holds row m of the dW tile; pushing straight from
@@ -364,7 +412,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // thread pays for a system-scope fence instead of all 128 (measured: 14 us -> 4 us for this kernel).
         named_bar_sync(1, 128);
         if (threadIdx.x == 64)
-          st_release_sys_u32(r.flags + p.push_item_base + blockIdx.x * gridDim.y + blockIdx.y, r.seq);
+          st_release_scoped_u32(r.flags + p.push_item_base + blockIdx.x * gridDim.y + blockIdx.y, r.seq,
+                                p.push.gpu_scope);
       }
     }
   }

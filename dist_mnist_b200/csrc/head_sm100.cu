@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
     // the CTA barrier orders every thread's P2P stores before thread 0's cumulative system-scope release
     __syncthreads();
     if (tid == 0) {
-      fence_acq_rel_sys();
+      fence_acq_rel_scoped(p.push.gpu_scope);
       st_relaxed_sys_u32(r.flags + p.item_w_last_base + blockIdx.x, seq);
       st_relaxed_sys_u32(rb.flags + p.item_b_hidden_base + blockIdx.x, seq);
       if (blockIdx.x == 0) st_relaxed_sys_u32(rl.flags + p.item_b_last, seq);

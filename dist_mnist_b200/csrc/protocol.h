@@ -32,6 +32,8 @@ struct PushTarget {
   uint32_t* flags;          // MAILBOX: this worker's slot-0 flag array on the PS
   uint32_t flag_slot_stride;
   uint32_t nslots;
+  uint32_t gpu_scope;       // 1: the PS shard lives on this worker's own GPU -> gpu-scope release is enough
+  uint32_t pad_;
   const uint32_t* seq_ptr;  // device-local current push sequence number (1-based); null => seq 1 / slot 0
 };
 
@@ -162,6 +164,8 @@ struct PsServeParams {
   // patches entries while the kernel runs when a worker attaches late, so it is read with volatile loads.
   uint32_t* volatile* inbox_table;
   uint32_t* exit_counter;      // CTAs increment on exit (debug / clean shutdown)
+  uint32_t gpu_scope;          // 1: every worker runs on the PS's own GPU (flags / acks at gpu scope)
+  uint32_t pad_;
 };
 
 }  // namespace dm

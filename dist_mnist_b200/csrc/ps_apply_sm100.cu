@@ -147,8 +147,8 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
         if (lane < P.n_workers) {
           seq = P.next_seq[static_cast<size_t>(lane) * P.n_items + item];
           const uint32_t slot = seq % P.nslots;
-          const uint32_t f =
-              ld_acquire_sys_u32(P.flags + (static_cast<size_t>(lane) * P.nslots + slot) * P.n_items + item);
+          const uint32_t f = ld_acquire_scoped_u32(
+              P.flags + (static_cast<size_t>(lane) * P.nslots + slot) * P.n_items + item, P.gpu_scope);
           ready = (f == seq) ? 1u : 0u;
           s_seq[lane] = seq;
         }
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
               uint32_t* ib = P.inbox_table[w];
               if (ib != nullptr) {
                 reinterpret_cast<volatile uint32_t*>(ib)[1] = gs;
-                st_release_sys_u32(ib, seq);  // ack: the mailbox slot may be reused
+                st_release_scoped_u32(ib, seq, P.gpu_scope);  // ack: the mailbox slot may be reused
               }
             }
           }

@@ -69,6 +69,7 @@ class ParameterServer:
         self.n_workers = cluster.num_workers
         self.lib = N.lib()
         self._attached: Dict[int, Segment] = {}
+        self._attached_devices: List[int] = []
         self._serving = False
         self._cpu_handle = None
         self._stream = None
@@ -135,6 +136,9 @@ class ParameterServer:
         P.host_stop = s.addr("ctrl", 4 * CTRL_HOST_STOP)
         P.exit_counter = s.addr("ctrl", 4 * CTRL_EXIT_COUNTER)
         P.worker_done = s.addr("ctrl", 4 * CTRL_WORKER_DONE)
+        # flags / acks need system scope only when some worker sits on another GPU
+        P.gpu_scope = int(cfg.backend == "cuda" and self.n_workers == 1 and len(self._attached_devices) == 1
+                          and self._attached_devices[0] == self.device)
         if cfg.backend == "cuda":
             P.inbox_table = s.addr("inbox_table")
         else:
@@ -202,6 +206,7 @@ class ParameterServer:
                     continue
                 seg = Segment.open(desc, device=self.device)
                 self._attached[w] = seg
+                self._attached_devices.append(desc.get("worker_device", -1))
                 ptr = seg.addr("inbox", 8 * desc["inbox_index"][str(self.task_index)]) \
                     if str(self.task_index) in desc["inbox_index"] else 0
                 if ptr:

@@ -111,6 +111,7 @@ class Worker:
                                   tag=f"w{self.task_index}")
         desc = self.seg.export()
         desc["inbox_index"] = {str(k): i for k, i in self.inbox_index.items()}
+        desc["worker_device"] = self.device
         self.rdv.put(f"worker/{self.task_index}/inbox", desc)
         self._connected = True
 
@@ -271,6 +272,9 @@ class Worker:
             t.flag_slot_stride = ni
             t.nslots = ns
         t.seq_ptr = self.seg.addr("seq")
+        # ps shard on our own GPU (in-process / colocated): gpu-scope release suffices for its flags
+        t.gpu_scope = int(self.cfg.backend == "cuda" and desc.get("device", -2) == self.device
+                          and self.cluster.num_workers == 1)
         return t
 
     def _weight_ptr(self, vl: VarLayout) -> int:
