@@ -136,6 +136,13 @@ def main(argv=None) -> int:
             rdv = Rendezvous(cluster, "ps", rank)
             ps = ParameterServer(cluster, rank, spec, opt, cfg, device=local_rank, rdv=rdv)
             ps.start()
+            # workers register in any order; keep attaching (what `ps.join()` does in the CLI) until all are in
+            t_att = time.time()
+            while len(ps._attached) < n_workers:
+                ps.attach_registered_workers()
+                if time.time() - t_att > 240:
+                    raise SystemExit(f"ps {rank}: only {len(ps._attached)}/{n_workers} workers registered")
+                time.sleep(0.01)
             ps_list = [ps]
         else:
             w = rank - num_ps

@@ -154,6 +154,14 @@ def main() -> int:
                     "tmem_full seen", "-", "epilogue done", "exit"]
         for p_ in plans:
             if not hasattr(p_, "tm_a"):
+                p_.params.debug_ts = ts.data_ptr()
+                for _ in range(3):
+                    p_.launch(N.current_stream_ptr())
+                torch.cuda.synchronize()
+                t = ts.tolist()
+                lab = ["seq+ack", "staged (A)", "logits+softmax (B+C)", "grads (D)", "pushed+sync", "flags out"]
+                print("head: " + "  ".join(f"{lab[i - 1]}=+{t[i] - t[0]}" for i in range(1, 7)) + " (SM cycles)")
+                p_.params.debug_ts = None
                 continue
             p_.params.debug_ts = ts.data_ptr()
             for _ in range(3):

@@ -60,6 +60,7 @@ class GemmParams(C.Structure):
         ("splitk_scratch", C.c_void_p),
         ("splitk_counter", C.c_void_p),
         ("debug_ts", C.c_void_p),
+        ("splitk_cluster", C.c_int), ("pad2_", C.c_int),
     ]
 
 
@@ -79,6 +80,7 @@ class HeadParams(C.Structure):
         ("result", C.c_void_p),
         ("seq_ptr", C.c_void_p), ("inbox", C.c_void_p), ("ps_global_step", C.c_void_p),
         ("nslots", C.c_uint32), ("n_inbox", C.c_uint32),
+        ("debug_ts", C.c_void_p),
     ]
 
 
@@ -150,7 +152,7 @@ def _declare(l: C.CDLL) -> None:
         "dm_stream_sync": (i, [vp]),
         "dm_stream_query": (i, [vp]),
         "dm_make_tensor_map_2d": (i, [vp, vp, i, u64, u64, u64, u32, u32, i]),
-        "dm_gemm_smem_bytes": (i, [i, i]),
+        "dm_gemm_smem_bytes": (i, [i, i, i]),
         "dm_launch_gemm": (i, [vp, vp, vp, i, i, i, i, vp]),
         "dm_launch_head": (i, [vp, vp]),
         "dm_launch_accuracy": (i, [vp, vp, i, i, vp, vp]),

@@ -15,7 +15,7 @@
 #include "protocol.h"
 
 namespace dm {
-size_t gemm_smem_bytes(int bn, int stages);
+size_t gemm_smem_bytes(int bn, int stages, int cluster);
 cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int dtype, bool a_mn,
                         bool b_mn, int splits, cudaStream_t stream);
 size_t head_smem_bytes(int B_pad, int H, int C);
@@ -194,7 +194,9 @@ int dm_make_tensor_map_2d(void* out, void* gptr, int dtype, uint64_t dim0, uint6
 // ------------------------------------------------------------------------------------------
 // kernel launches
 // ------------------------------------------------------------------------------------------
-int dm_gemm_smem_bytes(int bn, int stages) { return static_cast<int>(dm::gemm_smem_bytes(bn, stages)); }
+int dm_gemm_smem_bytes(int bn, int stages, int cluster) {
+  return static_cast<int>(dm::gemm_smem_bytes(bn, stages, cluster));
+}
 
 // Once per device, before any launch / graph capture: opt the big-smem kernels into their dynamic smem sizes.
 int dm_prepare_kernels(int dev) {

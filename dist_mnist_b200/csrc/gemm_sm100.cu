@@ -95,6 +95,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full_bar = empty_bar + stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  // cluster split-K: landing zone for the partial columns the *other* CTAs of the cluster send us through
+  // distributed shared memory: red[src rank][my column][tile row], then csum[src rank][tile row]
+  float* red = reinterpret_cast<float*>(smem + ring_bytes + 256);
+  float* csum = red + (bn + 8) * kTileM;   // nsplit * ceil(bn / nsplit) <= bn + 8 landing columns
+  const bool cluster_mode = p.splitk_cluster != 0 && gridDim.z > 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -136,6 +141,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  // Distributed shared memory of a peer CTA may only be touched once that CTA is known to be running:
+  // everybody arrives here, and waits right before its first remote access / at the end of its role.
+  if (cluster_mode) cluster_barrier_arrive_release();
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
@@ -166,6 +174,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (dbg && i == 0) dbg[2] = clock64();
       }
     }
+    __syncwarp();
+    if (cluster_mode) cluster_barrier_wait_acquire();
   } else if (warp == 1) {
     // ===================== MMA issuer (one elected lane) =====================
     const uint32_t idesc = make_idesc(MmaKind<T>::kFormat, A_MN, B_MN, kTileM, bn);
@@ -193,14 +203,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       __syncwarp();
     }
+    if (cluster_mode) cluster_barrier_wait_acquire();
   } else {
     // ===================== epilogue warps (TMEM -> registers -> global / peer) =====================
     // the bias (a peer load from the PS shard) is requested before the accumulator wait so that its NVLink
     // round trip overlaps the K loop
     const int m_pref = m0 + (warp & 3) * 32 + lane;
     const float bias_pref = (p.epi == EPI_TRANSPOSED && p.bias != nullptr && m_pref < p.M) ? p.bias[m_pref] : 0.f;
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
+    if (nkc > 0) {  // a cluster may contain a CTA without k-chunks (K not a multiple of the split): zeros
+      mbar_wait(tmem_full_bar, 0);
+      tcgen05_fence_after();
+    }
     if (dbg && threadIdx.x == 64) dbg[5] = clock64();
     const int q = warp & 3;
     const int m = m0 + q * 32 + lane;
@@ -214,7 +227,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int nsplit = gridDim.z;
       bool finalize = true;
       float* part_base = nullptr;
-      if (nsplit > 1) {
+      if (cluster_mode) {
+        // ---- cluster split-K, phase 1 (reduce-scatter): CTA r of the cluster owns columns [r*cw, (r+1)*cw) of
+        // the tile. Every lane sends each of its accumulator values to the owner's shared memory with
+        // st.shared::cluster (coalesced over the 32 lanes of a warp); after the cluster barrier every CTA sums
+        // the nsplit contributions for its own columns. No global-memory round trip, no atomics.
+        cluster_barrier_wait_acquire();   // all CTAs of the cluster are up (arrived after their prologue)
+        const uint32_t crank = cluster_ctarank();
+        const int cw = (bn + nsplit - 1) / nsplit;
+        const uint32_t red_local = smem_u32(red) + ((crank * cw) * kTileM + q * 32 + lane) * 4u;
+        int dest = 0, cc = 0;
+        for (int c0 = 0; c0 < bn; c0 += 16) {
+          float v[16];
+          if (nkc > 0) {
+            tmem_ld_32x32b_x16(taddr + c0, v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t ra = mapa_shared_cluster(red_local + static_cast<uint32_t>(cc * kTileM) * 4u, dest);
+            st_shared_cluster_f32(ra, v[j]);
+            if (++cc == cw) { cc = 0; ++dest; }
+          }
+        }
+        finalize = false;  // phase 2 runs after the cluster barrier below
+      } else if (nsplit > 1) {
         // scratch layout [mtile][split][n][128] with the tile row (= lane) fastest: every warp store / load below
         // is one fully used 128-byte line (the row-per-thread layout cost 32 line transactions per instruction
         // and made the fix-up take 8 us).
@@ -418,6 +457,61 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   }
 
+  if (cluster_mode) {
+    // every thread of every CTA of the cluster: partial columns have landed after this barrier
+    cluster_barrier_arrive_release();
+    cluster_barrier_wait_acquire();
+    const int nsplit = gridDim.z;
+    const uint32_t crank = cluster_ctarank();
+    const int cw = (bn + nsplit - 1) / nsplit;
+    float colsum = 0.f;
+    if (warp >= 2) {
+      // ---- phase 2: sum the nsplit contributions of my columns and run the real epilogue on them ----
+      const int q = warp & 3;
+      const int mrow = q * 32 + lane;
+      const int m = m0 + mrow;
+      const bool m_ok = m < p.M;
+      const float bias = (p.bias != nullptr && m_ok) ? p.bias[m] : 0.f;
+      for (int cc = 0; cc < cw; ++cc) {
+        const int c = static_cast<int>(crank) * cw + cc;
+        if (c >= bn) break;
+        float acc = 0.f;
+        for (int src = 0; src < nsplit; ++src) acc += red[(src * cw + cc) * kTileM + mrow];
+        const int n = n0 + c;
+        if (n < p.N && m_ok) {
+          float val = acc + bias;
+          if (p.relu) val = fmaxf(val, 0.f);
+          if (p.mask != nullptr) {
+            const float a = p.mask_bf16
+                                ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(
+                                      p.mask)[static_cast<size_t>(n) * p.ldmask + m])
+                                : reinterpret_cast<const float*>(p.mask)[static_cast<size_t>(n) * p.ldmask + m];
+            val = a > 0.f ? val : 0.f;
+          }
+          colsum += val;
+          const size_t o = static_cast<size_t>(n) * p.ldo + m;
+          if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(val);
+          else reinterpret_cast<float*>(p.out)[o] = val;
+        }
+      }
+      if (p.has_colsum) {
+        // bias-gradient partial sums of my columns -> CTA 0 of the cluster
+        const uint32_t ca = mapa_shared_cluster(smem_u32(csum) + (crank * kTileM + mrow) * 4u, 0);
+        st_shared_cluster_f32(ca, colsum);
+      }
+    }
+    if (p.has_colsum) {
+      cluster_barrier_arrive_release();
+      cluster_barrier_wait_acquire();
+      if (crank == 0 && warp >= 2) {
+        const int mrow = (warp & 3) * 32 + lane;
+        float tot = 0.f;
+        for (int src = 0; src < nsplit; ++src) tot += csum[src * kTileM + mrow];
+        epilogue_colsum(p, tot, m0 + mrow, m0 + mrow < p.M);
+      }
+    }
+  }
+
   if (dbg && threadIdx.x == 64) dbg[7] = clock64();
   tcgen05_fence_before();
   __syncthreads();
@@ -430,11 +524,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-size_t gemm_smem_bytes(int bn, int stages) {
+size_t gemm_smem_bytes(int bn, int stages, int cluster) {
   size_t ring = static_cast<size_t>(stages) * (kABytes + bn * 128);
   const size_t stage_tile = static_cast<size_t>(kTileM) * (bn + 4) * sizeof(float);  // push-epilogue transpose tile
   if (ring < stage_tile) ring = (stage_tile + 1023) & ~size_t(1023);
-  return ring + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+  size_t total = ring + 256 /* barriers + tmem slot */ + 1024 /* alignment slack */;
+  if (cluster) total += static_cast<size_t>(bn + 8) * kTileM * sizeof(float) + 8 * kTileM * sizeof(float);  // red + csum
+  return total;
 }
 
 constexpr int kMaxDynSmem = 226 * 1024;  // 227 KB per-block limit minus the kernel's static shared memory
@@ -464,10 +560,27 @@ template <typename T, bool A_MN, bool B_MN>
 static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, dim3 grid,
                               cudaStream_t stream) {
   auto kern = gemm_tcgen05_kernel<T, A_MN, B_MN>;
-  const size_t smem = gemm_smem_bytes(p.bn, p.stages);
+  const bool cluster = p.splitk_cluster != 0 && grid.z > 1;
+  const size_t smem = gemm_smem_bytes(p.bn, p.stages, cluster ? 1 : 0);
   if (smem > static_cast<size_t>(kMaxDynSmem)) return cudaErrorInvalidValue;
-  kern<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p);
-  return cudaGetLastError();
+  if (!cluster) {
+    kern<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p);
+    return cudaGetLastError();
+  }
+  if (grid.z > 8 || (2 * p.stages + 1) * sizeof(uint64_t) + 16 > 256) return cudaErrorInvalidValue;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;   // the K-splits of one output tile form a cluster
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = grid.z;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
 }
 
 // dtype: 0 = fp32 (tf32 MMA), 1 = bf16

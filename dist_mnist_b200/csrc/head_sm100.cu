@@ -99,6 +99,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
   float* sRed = sHs + p.B_pad * kHeadSlice;      // [64] block reductions
   __shared__ uint32_t s_seq;
   __shared__ uint32_t s_gstep;
+  long long* dbg = (p.debug_ts != nullptr && blockIdx.x == 0) ? p.debug_ts : nullptr;
+  if (dbg && tid == 0) dbg[0] = clock64();
 
   if (tid == 0) {
     uint32_t seq = p.seq_ptr ? *reinterpret_cast<volatile uint32_t*>(p.seq_ptr) : 1u;
@@ -127,6 +129,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
       gstep = inbox[1] + (seq - ack);
     }
     s_gstep = gstep;
+    if (dbg) dbg[1] = clock64();   // seq read + ack wait done
   }
 
   // ---- phase A: stage W_last (peer loads from the PS shard) and this CTA's slice of h ----
@@ -139,6 +142,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
     sHs[i] = (b < B && h0 + hh < H) ? ld_act(p.h, static_cast<size_t>(b) * p.ldh + h0 + hh, p.act_bf16) : 0.f;
   }
   __syncthreads();
+  if (dbg && tid == 0) dbg[2] = clock64();
   const uint32_t seq = s_seq;
 
   // ---- phase B+C: logits, softmax, loss, accuracy and dlogits. thread -> (row b, class c): the 16 lanes of a
@@ -237,6 +241,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
 #pragma unroll
   for (int c = 0; c < kMaxC; ++c) wcol[c] = sW[c * ldw + min(h, H - 1)];
   __syncthreads();
+  if (dbg && tid == 0) dbg[3] = clock64();
 
   if (blockIdx.x == 0 && tid == 0) {
     float l = 0.f, cr = 0.f;
@@ -285,6 +290,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
     dst[kMaxC] = dbh;
   }
   __syncthreads();
+  if (dbg && tid == 0) dbg[4] = clock64();
   const ResolvedPushH r = resolve_push_h(p.push, seq);
   const ResolvedPushH rb = resolve_push_h(p.push_bh, seq);
   const ResolvedPushH rl = resolve_push_h(p.push_bl, seq);
@@ -311,6 +317,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
   if (p.push.mode == PUSH_MAILBOX) {
     // the CTA barrier orders every thread's P2P stores before thread 0's cumulative system-scope release
     __syncthreads();
+    if (dbg && tid == 0) dbg[5] = clock64();
     if (tid == 0) {
       fence_acq_rel_scoped(p.push.gpu_scope);
       st_relaxed_sys_u32(r.flags + p.item_w_last_base + blockIdx.x, seq);
@@ -318,6 +325,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
       if (blockIdx.x == 0) st_relaxed_sys_u32(rl.flags + p.item_b_last, seq);
     }
   }
+  if (dbg && tid == 0) dbg[6] = clock64();
 }
 
 size_t head_smem_bytes(int B_pad, int H, int C) {

@@ -72,6 +72,8 @@ struct GemmParams {
   float* splitk_scratch;     // gridDim.z > 1: [mtiles][splits][128][bn] fp32 partial tiles
   uint32_t* splitk_counter;  // gridDim.z > 1: [mtiles] arrival counters (self-resetting)
   long long* debug_ts;       // optional: 9 clock64() phase stamps of CTA (0,0,0); null in production
+  int splitk_cluster;        // 1: the gridDim.z splits of a tile form one thread-block cluster and reduce
+  int pad2_;                 //    their partial accumulators through distributed shared memory
 };
 
 // Softmax-cross-entropy head (last dense layer + loss + its gradients), see head_sm100.cu
@@ -116,6 +118,7 @@ struct HeadParams {
   uint32_t* ps_global_step;  // peer pointer (atomic mode: atom.add; local mode: null)
   uint32_t nslots;
   uint32_t n_inbox;          // number of PS shards this worker pushes to
+  long long* debug_ts;       // optional clock64() phase stamps of CTA 0; null in production
 };
 
 // One unit of PS apply work.

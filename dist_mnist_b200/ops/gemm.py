@@ -88,7 +88,7 @@ class GemmPlan:
 
     @property
     def smem_bytes(self) -> int:
-        return N.lib().dm_gemm_smem_bytes(self.params.bn, self.params.stages)
+        return N.lib().dm_gemm_smem_bytes(self.params.bn, self.params.stages, int(self.params.splitk_cluster))
 
 
 def _pick_stages(bn: int, kc: int) -> int:
@@ -105,8 +105,26 @@ def auto_splits(K: int, dtype: int, mtiles: int) -> int:
     return max(1, min(8, ceil_div(kc, 3), max(1, 96 // max(1, mtiles))))
 
 
+def cluster_splits(K: int, dtype: int) -> int:
+    """Cluster size (power of two <= 8) for the DSMEM split-K: ~3-4 k-chunks per CTA."""
+    kc = ceil_div(K, bke(dtype))
+    if kc >= 16:
+        return 8
+    if kc >= 8:
+        return 4
+    if kc >= 4:
+        return 2
+    return 1
+
+
+def splitk_mode(bn: int) -> str:
+    """'cluster' (thread-block cluster + distributed shared memory reduce-scatter, bn <= 64) or 'global'."""
+    mode = os.environ.get("DM_SPLITK", "cluster")
+    return mode if (mode != "cluster" or bn <= 64) else "global"
+
+
 def _attach_splitk(plan: "GemmPlan", mtiles: int, splits: int, bn: int) -> None:
-    if splits <= 1:
+    if splits <= 1 or plan.params.splitk_cluster:
         return
     import torch
 
@@ -144,9 +162,14 @@ def forward_plan(*, w_ptr: int, x_ptr: int, out_ptr: int, bias_ptr: int, O: int,
     tm_a = N.make_tensor_map(w_ptr, dtype, I, O, ldw * es, k, TILE_M)
     tm_b = N.make_tensor_map(x_ptr, dtype, I, B_pad, ldx * es, k, B_pad)
     mtiles = ceil_div(O, TILE_M)
-    splits = auto_splits(I, dtype, mtiles) if splits is None else splits
+    cluster = splitk_mode(B_pad) == "cluster"
+    if splits is None:
+        splits = cluster_splits(I, dtype) if cluster else auto_splits(I, dtype, mtiles)
+    cluster = cluster and 1 < splits <= 8
     p = _base_params(O, B, I, B_pad, dtype, splits)
-    splits = ceil_div(ceil_div(I, k), p.kc_per_split)  # drop empty trailing splits
+    if not cluster or os.environ.get("DM_CLUSTER_TRIM", "0") == "1":
+        splits = ceil_div(ceil_div(I, k), p.kc_per_split)  # drop empty trailing splits
+    p.splitk_cluster = int(cluster and splits > 1)
     p.epi = N.EPI_TRANSPOSED
     p.out = out_ptr
     p.out_bf16 = int(dtype == N.DT_BF16)
@@ -205,9 +228,14 @@ def dx_plan(*, w_ptr: int, dy_ptr: int, out_ptr: int, mask_ptr: int, O: int, I: 
     tm_a = N.make_tensor_map(w_ptr, dtype, I, O, ldw * es, k, k, mn_major=True)
     tm_b = N.make_tensor_map(dy_ptr, dtype, O, B_pad, lddy * es, k, B_pad)
     mtiles = ceil_div(I, TILE_M)
-    splits = auto_splits(O, dtype, mtiles) if splits is None else splits
+    cluster = splitk_mode(B_pad) == "cluster"
+    if splits is None:
+        splits = cluster_splits(O, dtype) if cluster else auto_splits(O, dtype, mtiles)
+    cluster = cluster and 1 < splits <= 8
     p = _base_params(I, B, O, B_pad, dtype, splits)
-    splits = ceil_div(ceil_div(O, k), p.kc_per_split)
+    if not cluster or os.environ.get("DM_CLUSTER_TRIM", "0") == "1":
+        splits = ceil_div(ceil_div(O, k), p.kc_per_split)
+    p.splitk_cluster = int(cluster and splits > 1)
     p.epi = N.EPI_TRANSPOSED
     p.out = out_ptr
     p.out_bf16 = int(dtype == N.DT_BF16)

@@ -33,7 +33,8 @@ class EngineConfig:
     apply_mode: str = "per_push"     # "per_push" (reference semantics) | "merged"
     push_mode: str = "mailbox"       # "mailbox" (PS kernel applies; Adam or SGD) | "atomic" (SGD red.add, no PS kernel)
     sharding: str = "round_robin"    # "round_robin" (reference parity) | "byte_balanced"
-    ps_ctas: int = 32                # CTAs of the persistent PS kernel
+    ps_ctas: int = 0                 # CTAs of the persistent PS kernel (0 = auto: 120 on a dedicated ps GPU,
+                                     # 32 when a worker shares the GPU)
     pipeline_slots: int = 4          # worker executor ring depth
     colocate: bool = False           # worker i shares GPU i with ps i (N workers on N GPUs)
 

@@ -171,7 +171,7 @@ class ParameterServer:
             self._ctl_stream = out.value
             N.check(self.lib.dm_host_alloc(4096, C.byref(out)))
             self._pin = out.value
-            n_ctas = max(1, min(self.cfg.ps_ctas, self.shard.n_items))
+            n_ctas = self._serve_ctas()
             N.check(self.lib.dm_launch_ps_serve(C.addressof(P), n_ctas, self._stream), "launch ps_serve")
         else:
             self._cpu_handle = self.lib.dm_cpu_ps_start(C.addressof(P))
@@ -249,6 +249,15 @@ class ParameterServer:
                 self._cpu_handle = None
         self._serving = False
 
+    def _serve_ctas(self) -> int:
+        """One item per CTA where possible: a dedicated ps GPU gives the serve kernel (almost) every SM, a GPU
+        shared with a worker keeps most SMs for the worker's step kernels."""
+        want = self.cfg.ps_ctas
+        if want <= 0:
+            shared = any(d == self.device for d in self._attached_devices)
+            want = 32 if shared else 120
+        return max(1, min(want, self.shard.n_items))
+
     def restart(self) -> None:
         """Relaunch the serve kernel / loop after `stop()` (all shard state lives in the segment, so serving
         resumes exactly where it stopped). Used by the benchmark to bracket timed regions with a full device
@@ -262,7 +271,7 @@ class ParameterServer:
             N.check(self.lib.dm_set_device(self.device), "set device")
             N.check(self.lib.dm_memset_async(self.seg.addr("ctrl", 4 * CTRL_HOST_STOP), 0, 4, self._ctl_stream))
             N.check(self.lib.dm_stream_sync(self._ctl_stream))
-            n_ctas = max(1, min(self.cfg.ps_ctas, self.shard.n_items))
+            n_ctas = self._serve_ctas()
             N.check(self.lib.dm_launch_ps_serve(C.addressof(self._P), n_ctas, self._stream), "launch ps_serve")
         else:
             self.lib.dm_store_release_u32(self.seg.addr("ctrl", 4 * CTRL_HOST_STOP), 0)
