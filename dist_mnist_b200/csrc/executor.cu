@@ -155,7 +155,8 @@ int dm_exec_create(int device, int nslots, size_t x_bytes, size_t y_bytes, void*
     s.y_dev = static_cast<uint8_t*>(s.x_dev) + x_al;
     EX_CUDA(cudaMalloc(reinterpret_cast<void**>(&s.res_dev), sizeof(dm::StepResult)));
     EX_CUDA(cudaMemset(s.res_dev, 0, sizeof(dm::StepResult)));
-    EX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&s.res_host), sizeof(dm::StepResult), cudaHostAllocDefault));
+    EX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&s.res_host), sizeof(dm::StepResult),
+                          cudaHostAllocMapped | cudaHostAllocPortable));  // written by the head kernel over PCIe
     EX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&s.x_stage), x_al + y_bytes, cudaHostAllocDefault));
     s.y_stage = s.x_stage + x_al;
     memset(s.res_host, 0, sizeof(dm::StepResult));
@@ -172,7 +173,9 @@ int dm_exec_slot_info(void* h, int slot, void** x_dev, void** y_dev, void** res_
   ExecSlot& s = ex->slots.at(slot);
   *x_dev = s.x_dev;
   *y_dev = s.y_dev;
-  *res_dev = s.res_dev;
+  // The step result is written by the head kernel straight into pinned (UVA-mapped) host memory: a 16-byte
+  // posted PCIe write instead of a D2H memcpy node that would add a copy-engine round trip to every step.
+  *res_dev = s.res_host;
   *x_stage = s.x_stage;
   *y_stage = s.y_stage;
   return 0;
@@ -192,8 +195,7 @@ int dm_exec_begin_capture(void* h, int slot) {
 int dm_exec_end_capture(void* h, int slot, int kernels_in_graph) {
   Executor* ex = static_cast<Executor*>(h);
   ExecSlot& s = ex->slots.at(slot);
-  // last node of every step: 16-byte result D2H into pinned memory (loss, global_step, correct, seq)
-  EX_CUDA(cudaMemcpyAsync(s.res_host, s.res_dev, sizeof(dm::StepResult), cudaMemcpyDeviceToHost, ex->compute));
+  // (no D2H node: the head kernel stores the 16-byte StepResult directly into s.res_host, see slot_info)
   EX_CUDA(cudaStreamEndCapture(ex->compute, &s.graph));
   EX_CUDA(cudaGraphInstantiate(&s.exec, s.graph, 0));
   ex->kernels_per_graph = kernels_in_graph;
