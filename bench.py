@@ -53,6 +53,8 @@ def parse_args(argv=None):
     p.add_argument("--num_ps", type=int, default=1)
     p.add_argument("--sharding", choices=["round_robin", "byte_balanced"], default="round_robin")
     p.add_argument("--nslots", type=int, default=2)
+    p.add_argument("--lanes", type=int, default=2,
+                   help="steps of one worker in flight on its GPU at once (async SGD; must be <= nslots)")
     p.add_argument("--skip_e2e", action="store_true")
     return p.parse_args(argv)
 
@@ -95,7 +97,8 @@ def main(argv=None) -> int:
     spec = mlp.get_model(args.model, args.hidden_units)
     opt = OptimizerConfig(args.optimizer, args.learning_rate)
     cfg = EngineConfig(backend="cuda", dtype=args.dtype, nslots=args.nslots, apply_mode=args.apply_mode,
-                       push_mode=args.push_mode, sharding=args.sharding)
+                       push_mode=args.push_mode, sharding=args.sharding, lanes=args.lanes,
+                       pipeline_slots=max(4, 2 * args.lanes))
     cfg.validate(opt)
     K, W, B = args.steps, args.warmup, args.batch_size
 
@@ -191,6 +194,7 @@ def main(argv=None) -> int:
                 rdv_any.wait_count(f"bench/{ph}/serving", args.num_ps)
 
     elapsed_ms = 0.0
+    host_enqueue_ms = 0.0
     e2e_s = 0.0
     h2d_bytes = d2h_bytes = 0
     if worker is not None:
@@ -214,7 +218,10 @@ def main(argv=None) -> int:
     if worker is not None:
         timer = StreamTimer(worker.compute_stream, local_rank)
         timer.start()
+        worker.fork_lanes()   # no lane starts a timed step before the start event
+        t_host = time.perf_counter()
         resident_steps(K, max(W, 3))
+        host_enqueue_ms = (time.perf_counter() - t_host) * 1e3
         worker.enqueue_wait_ack()
         timer.stop()
         elapsed_ms = timer.elapsed_ms()
@@ -242,7 +249,7 @@ def main(argv=None) -> int:
     # ---------------- reduce over ranks ----------------
     kps = worker.kernels_per_step if worker is not None else 0
     stats = torch.tensor([elapsed_ms, e2e_s, float(launches), float(h2d_bytes), float(d2h_bytes), float(final_step),
-                          float(kps)], dtype=torch.float64, device="cuda")
+                          float(kps), host_enqueue_ms], dtype=torch.float64, device="cuda")
     mx = stats.clone()
     sm = stats.clone()
     if world > 1:
@@ -275,6 +282,8 @@ def main(argv=None) -> int:
                                 + (" (ps and worker share the GPU)" if world == 1 else " (dedicated ps GPU)")),
                 "optimizer": f"{args.optimizer} lr={args.learning_rate}",
                 "apply": f"{args.push_mode}/{args.apply_mode}",
+                "steps_in_flight_per_worker": args.lanes,
+                "host_enqueue_us_per_step": round(float(mx[7]) * 1e3 / K, 2),
                 "l2_policy": "inputs stream from a 55000x784 device-resident dataset (172 MB fp32 > 126 MB L2); "
                              "parameters (0.3 MB) stay L2-resident as in real training",
                 "global_step_after_run": int(mx[5]),

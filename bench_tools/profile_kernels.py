@@ -39,6 +39,7 @@ def main() -> int:
     ap.add_argument("--push", default="mailbox", choices=["mailbox", "local", "atomic"])
     ap.add_argument("--phases", action="store_true", help="print in-kernel phase timestamps of the GEMM kernels")
     ap.add_argument("--fwd_splits", type=int, default=None)
+    ap.add_argument("--pdl", action="store_true", help="programmatic dependent launch for every kernel but the first")
     args = ap.parse_args()
     dev = "cuda"
     spec = mlp.get_model(args.model)
@@ -118,6 +119,10 @@ def main() -> int:
                                       mask_ptr=act[l].data_ptr(), O=fout, I=fin, B=B, B_pad=B_pad, dtype=dt,
                                       ldw=wl.ld, lddy=dact[l + 1].shape[1], ldo=dact[l].shape[1], colsum=push,
                                       colsum_offset=pb.offset, colsum_item_base=pb.item_base, name=f"dx{l}"))
+
+    if args.pdl:
+        for p_ in plans[1:]:
+            p_.params.pdl = 1
 
     # PS serve kernel configured for one worker; `worker_done` is advanced every iteration so that each launch
     # applies exactly the push that the step just published and then exits.

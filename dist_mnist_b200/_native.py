@@ -57,10 +57,11 @@ class GemmParams(C.Structure):
         ("push_offset", C.c_uint64),
         ("push_item_base", C.c_int), ("push_staged", C.c_int),
         ("bump_seq", C.c_void_p),
+        ("seq_counter", C.c_void_p),
         ("splitk_scratch", C.c_void_p),
         ("splitk_counter", C.c_void_p),
         ("debug_ts", C.c_void_p),
-        ("splitk_cluster", C.c_int), ("pad2_", C.c_int),
+        ("splitk_cluster", C.c_int), ("pdl", C.c_int),
     ]
 
 
@@ -76,7 +77,7 @@ class HeadParams(C.Structure):
         ("dpre", C.c_void_p),
         ("push", PushTarget), ("push_bl", PushTarget), ("push_bh", PushTarget),
         ("off_w_last", C.c_uint64), ("off_b_last", C.c_uint64), ("off_b_hidden", C.c_uint64),
-        ("item_w_last_base", C.c_int), ("item_b_last", C.c_int), ("item_b_hidden_base", C.c_int), ("pad_", C.c_int),
+        ("item_w_last_base", C.c_int), ("item_b_last", C.c_int), ("item_b_hidden_base", C.c_int), ("pdl", C.c_int),
         ("result", C.c_void_p),
         ("seq_ptr", C.c_void_p), ("inbox", C.c_void_p), ("ps_global_step", C.c_void_p),
         ("nslots", C.c_uint32), ("n_inbox", C.c_uint32),
@@ -183,7 +184,11 @@ def _declare(l: C.CDLL) -> None:
         "dm_loader_next": (None, [vp, vp, vp]),
         "dm_loader_epochs": (u64, [vp]),
         "dm_loader_destroy": (None, [vp]),
-        "dm_exec_create": (i, [i, i, sz, sz, C.POINTER(vp)]),
+        "dm_exec_create": (i, [i, i, i, sz, sz, C.POINTER(vp)]),
+        "dm_exec_lane_stream": (vp, [vp, i]),
+        "dm_exec_lanes": (i, [vp]),
+        "dm_exec_join": (i, [vp]),
+        "dm_exec_fork": (i, [vp]),
         "dm_exec_slot_info": (i, [vp, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "dm_exec_compute_stream": (vp, [vp]),
         "dm_exec_copy_stream": (vp, [vp]),

@@ -60,6 +60,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--apply_mode", choices=["per_push", "merged"], default="per_push")
     p.add_argument("--sharding", choices=["round_robin", "byte_balanced"], default="round_robin")
     p.add_argument("--nslots", type=int, default=2)
+    p.add_argument("--lanes", type=int, default=1,
+                   help="steps of this worker in flight at once (1 = like the reference: a step starts after the "
+                        "previous one's kernels; 2 overlaps consecutive steps, needs --nslots >= 2)")
     p.add_argument("--checkpoint_dir", type=str, default=None, help="chief checkpoints here (default: mkdtemp, DS:106)")
     p.add_argument("--save_checkpoint_secs", type=float, default=600.0)
     p.add_argument("--gpu", type=int, default=None, help="CUDA device for this task (default: ps k -> k, worker i -> num_ps+i)")
@@ -102,7 +105,7 @@ def run(args: argparse.Namespace) -> int:
     spec = mlp.get_model(args.model, args.hidden_units)
     opt = OptimizerConfig(args.optimizer, args.learning_rate)
     cfg = EngineConfig(backend=backend, dtype=args.dtype, nslots=args.nslots, apply_mode=args.apply_mode,
-                       push_mode=args.push_mode, sharding=args.sharding, colocate=args.colocate)
+                       push_mode=args.push_mode, sharding=args.sharding, colocate=args.colocate, lanes=args.lanes)
     cfg.validate(opt)
     device = -1
     if backend == "cuda":

@@ -272,6 +272,13 @@ __device__ __forceinline__ void cluster_barrier_wait_acquire() {
 }
 
 // Named barrier among a subset of warps (id 1..15; 0 is __syncthreads).
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute
+// may start while its predecessor in the stream is still running; `grid_dep_wait` blocks until the predecessor
+// grid has completed and its memory is visible, `grid_dep_launch` lets the successor start being scheduled.
+// Both are no-ops for kernels launched without the attribute.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

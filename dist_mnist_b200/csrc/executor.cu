@@ -15,8 +15,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "protocol.h"
@@ -83,13 +85,19 @@ constexpr size_t kHistory = 1 << 16;
 
 struct Executor {
   int device = 0;
-  cudaStream_t compute = nullptr, copy = nullptr;
+  // `lanes` compute streams: slot s runs on lane s % lanes, so up to `lanes` consecutive steps are in flight
+  // on the GPU at once (asynchronous SGD: a step does not wait for the previous step's push).
+  std::vector<cudaStream_t> compute;
+  std::vector<cudaEvent_t> lane_ev;
+  cudaStream_t copy = nullptr;
   std::vector<ExecSlot> slots;
+  cudaStream_t lane_of(size_t slot) const { return compute[slot % compute.size()]; }
   size_t x_bytes = 0, y_bytes = 0;
   uint64_t submitted = 0;  // tickets are 1-based
   std::vector<dm::StepResult> history;
   uint64_t launches = 0;
   int kernels_per_graph = 0;
+  std::vector<uint8_t*> ring;  // pinned x|y batches filled ahead by dm_exec_run's gather thread
 
   int retire(ExecSlot& s) {
     if (!s.in_flight) return 0;
@@ -136,14 +144,23 @@ void dm_loader_destroy(void* h) { delete static_cast<BatchLoader*>(h); }
 // ---------------------------------------------------------------------------------------------
 // executor
 // ---------------------------------------------------------------------------------------------
-int dm_exec_create(int device, int nslots, size_t x_bytes, size_t y_bytes, void** out) {
+int dm_exec_create(int device, int nslots, int lanes, size_t x_bytes, size_t y_bytes, void** out) {
   EX_CUDA(cudaSetDevice(device));
+  if (lanes < 1 || nslots < lanes || nslots % lanes != 0) {
+    g_exec_err = "executor: nslots must be a positive multiple of lanes";
+    return -1;
+  }
   Executor* ex = new Executor();
   ex->device = device;
   ex->x_bytes = x_bytes;
   ex->y_bytes = y_bytes;
   ex->history.resize(kHistory);
-  EX_CUDA(cudaStreamCreateWithFlags(&ex->compute, cudaStreamNonBlocking));
+  ex->compute.resize(lanes);
+  ex->lane_ev.resize(lanes);
+  for (int l = 0; l < lanes; ++l) {
+    EX_CUDA(cudaStreamCreateWithFlags(&ex->compute[l], cudaStreamNonBlocking));
+    EX_CUDA(cudaEventCreateWithFlags(&ex->lane_ev[l], cudaEventDisableTiming));
+  }
   EX_CUDA(cudaStreamCreateWithFlags(&ex->copy, cudaStreamNonBlocking));
   ex->slots.resize(nslots);
   for (auto& s : ex->slots) {
@@ -180,23 +197,43 @@ int dm_exec_slot_info(void* h, int slot, void** x_dev, void** y_dev, void** res_
   *y_stage = s.y_stage;
   return 0;
 }
-void* dm_exec_compute_stream(void* h) { return static_cast<Executor*>(h)->compute; }
+void* dm_exec_compute_stream(void* h) { return static_cast<Executor*>(h)->compute[0]; }
+void* dm_exec_lane_stream(void* h, int lane) { return static_cast<Executor*>(h)->compute.at(lane); }
+int dm_exec_lanes(void* h) { return static_cast<int>(static_cast<Executor*>(h)->compute.size()); }
+// Make lane 0 wait for everything submitted so far on the other lanes (stream-ordered join; used to close a
+// device-timed region or to order a follow-up kernel after all in-flight steps).
+int dm_exec_join(void* h) {
+  Executor* ex = static_cast<Executor*>(h);
+  for (size_t l = 1; l < ex->compute.size(); ++l) {
+    EX_CUDA(cudaEventRecord(ex->lane_ev[l], ex->compute[l]));
+    EX_CUDA(cudaStreamWaitEvent(ex->compute[0], ex->lane_ev[l], 0));
+  }
+  return 0;
+}
+// The reverse: every other lane waits for what has been enqueued on lane 0 so far (opens a timed region).
+int dm_exec_fork(void* h) {
+  Executor* ex = static_cast<Executor*>(h);
+  if (ex->compute.size() > 1) {
+    EX_CUDA(cudaEventRecord(ex->lane_ev[0], ex->compute[0]));
+    for (size_t l = 1; l < ex->compute.size(); ++l) EX_CUDA(cudaStreamWaitEvent(ex->compute[l], ex->lane_ev[0], 0));
+  }
+  return 0;
+}
 void* dm_exec_copy_stream(void* h) { return static_cast<Executor*>(h)->copy; }
 int dm_exec_nslots(void* h) { return static_cast<int>(static_cast<Executor*>(h)->slots.size()); }
 
 // Capture protocol: begin -> (Python launches the step's kernel plans on the compute stream) -> end.
 int dm_exec_begin_capture(void* h, int slot) {
   Executor* ex = static_cast<Executor*>(h);
-  (void)slot;
   EX_CUDA(cudaSetDevice(ex->device));
-  EX_CUDA(cudaStreamBeginCapture(ex->compute, cudaStreamCaptureModeRelaxed));
+  EX_CUDA(cudaStreamBeginCapture(ex->lane_of(slot), cudaStreamCaptureModeRelaxed));
   return 0;
 }
 int dm_exec_end_capture(void* h, int slot, int kernels_in_graph) {
   Executor* ex = static_cast<Executor*>(h);
   ExecSlot& s = ex->slots.at(slot);
   // (no D2H node: the head kernel stores the 16-byte StepResult directly into s.res_host, see slot_info)
-  EX_CUDA(cudaStreamEndCapture(ex->compute, &s.graph));
+  EX_CUDA(cudaStreamEndCapture(ex->lane_of(slot), &s.graph));
   EX_CUDA(cudaGraphInstantiate(&s.exec, s.graph, 0));
   ex->kernels_per_graph = kernels_in_graph;
   return 0;
@@ -217,21 +254,29 @@ int dm_exec_acquire_slot(void* h, int* slot) {
 int dm_exec_submit(void* h, const void* x_src, const void* y_src, uint64_t* ticket) {
   Executor* ex = static_cast<Executor*>(h);
   const uint64_t t = ex->submitted + 1;
-  ExecSlot& s = ex->slots[(t - 1) % ex->slots.size()];
+  const size_t slot_idx = (t - 1) % ex->slots.size();
+  ExecSlot& s = ex->slots[slot_idx];
+  cudaStream_t lane = ex->lane_of(slot_idx);
   if (ex->retire(s) != 0) return -1;
   if (x_src != nullptr) {
-    if (x_src == s.x_stage && y_src == s.y_stage) {
-      const size_t x_al = (ex->x_bytes + 255) & ~size_t(255);
-      EX_CUDA(cudaMemcpyAsync(s.x_dev, s.x_stage, x_al + ex->y_bytes, cudaMemcpyHostToDevice, ex->copy));
+    // Inputs travel on the copy stream so that step i+1's transfer overlaps step i's kernels. (Issuing the
+    // transfer on the step's own lane saves an event record / wait pair on the host but puts the copy's ~4 us
+    // latency on the lane's critical path: measured 14.2 -> 19.0 us/step with two lanes.)
+    cudaStream_t cs = ex->copy;
+    const size_t x_al = (ex->x_bytes + 255) & ~size_t(255);
+    if (static_cast<const uint8_t*>(y_src) == static_cast<const uint8_t*>(x_src) + x_al) {
+      EX_CUDA(cudaMemcpyAsync(s.x_dev, x_src, x_al + ex->y_bytes, cudaMemcpyDefault, cs));  // x|y packed like a slot
     } else {
-      EX_CUDA(cudaMemcpyAsync(s.x_dev, x_src, ex->x_bytes, cudaMemcpyDefault, ex->copy));
-      EX_CUDA(cudaMemcpyAsync(s.y_dev, y_src, ex->y_bytes, cudaMemcpyDefault, ex->copy));
+      EX_CUDA(cudaMemcpyAsync(s.x_dev, x_src, ex->x_bytes, cudaMemcpyDefault, cs));
+      EX_CUDA(cudaMemcpyAsync(s.y_dev, y_src, ex->y_bytes, cudaMemcpyDefault, cs));
     }
-    EX_CUDA(cudaEventRecord(s.in_ready, ex->copy));
-    EX_CUDA(cudaStreamWaitEvent(ex->compute, s.in_ready, 0));
+    if (cs != lane) {
+      EX_CUDA(cudaEventRecord(s.in_ready, ex->copy));
+      EX_CUDA(cudaStreamWaitEvent(lane, s.in_ready, 0));
+    }
   }
-  EX_CUDA(cudaGraphLaunch(s.exec, ex->compute));
-  EX_CUDA(cudaEventRecord(s.done, ex->compute));
+  EX_CUDA(cudaGraphLaunch(s.exec, lane));
+  EX_CUDA(cudaEventRecord(s.done, lane));
   s.ticket = t;
   s.in_flight = true;
   ex->submitted = t;
@@ -264,39 +309,77 @@ int dm_exec_drain(void* h) {
   for (auto& s : ex->slots)
     if (ex->retire(s) != 0) return -1;
   EX_CUDA(cudaStreamSynchronize(ex->copy));
-  EX_CUDA(cudaStreamSynchronize(ex->compute));
+  for (cudaStream_t c : ex->compute) EX_CUDA(cudaStreamSynchronize(c));
   return 0;
 }
 
-// The native train loop: n_steps x { loader.next -> pinned staging -> submit }, results of all steps are
-// written to out_results[n_steps] (drained at the end). stop_at_global_step > 0 ends the loop early once a
-// completed step reports global_step >= that value (StopAtStepHook semantics, reference DS:101); the number
-// of steps actually submitted is returned in *n_done.
+// The native train loop: n_steps x { next_batch -> pinned staging -> H2D -> step graph -> result }. A gather
+// thread runs the loader up to kAhead batches ahead into a ring of pinned x|y buffers while this thread submits,
+// so the per-step host cost is max(gather, submit) instead of their sum. Results of all steps are written to
+// out_results[n_steps] (drained at the end). stop_at_global_step > 0 ends the loop early once a completed step
+// reports global_step >= that value (StopAtStepHook semantics, reference DS:101); the number of steps actually
+// submitted is returned in *n_done (batches gathered ahead of an early stop are dropped).
 int dm_exec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uint32_t stop_at_global_step,
                 uint64_t* n_done) {
   Executor* ex = static_cast<Executor*>(h);
   BatchLoader* ld = static_cast<BatchLoader*>(loader);
   dm::StepResult* out = static_cast<dm::StepResult*>(out_results);
+  const size_t S = ex->slots.size();
+  const size_t x_al = (ex->x_bytes + 255) & ~size_t(255);
+  constexpr size_t kAhead = 4;
+  const size_t R = S + kAhead;
+  if (ex->ring.size() != R) {
+    for (uint8_t* b : ex->ring) cudaFreeHost(b);
+    ex->ring.assign(R, nullptr);
+    for (auto& b : ex->ring) {
+      EX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&b), x_al + ex->y_bytes, cudaHostAllocDefault));
+      memset(b, 0, x_al + ex->y_bytes);
+    }
+  }
+  // Ring buffer j % R was last read by the H2D copy of step j - R, which is complete once that step has been
+  // retired; submitting step t retires step t - S, hence the gather thread may fill batch j as soon as
+  // j < submitted + (R - S).
+  std::atomic<uint64_t> filled{0}, submitted{0};
+  std::atomic<bool> quit{false};
+  std::thread gather([&] {
+    for (uint64_t j = 0; j < n_steps && !quit.load(std::memory_order_relaxed); ++j) {
+      while (j >= submitted.load(std::memory_order_acquire) + kAhead) {
+        if (quit.load(std::memory_order_relaxed)) return;
+        std::this_thread::yield();
+      }
+      uint8_t* b = ex->ring[j % R];
+      ld->next(b, b + x_al);
+      filled.store(j + 1, std::memory_order_release);
+    }
+  });
   const uint64_t first = ex->submitted + 1;
   uint64_t harvested = 0;  // results [0, harvested) are final
   uint64_t i = 0;
   bool stop = false;
+  int rc = 0;
   for (; i < n_steps && !stop; ++i) {
-    ExecSlot& s = ex->slots[(ex->submitted) % ex->slots.size()];
-    if (ex->retire(s) != 0) return -1;  // staging buffer of this slot is free again
-    ld->next(s.x_stage, s.y_stage);
+    while (filled.load(std::memory_order_acquire) <= i) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    uint8_t* b = ex->ring[i % R];
     uint64_t t;
-    if (dm_exec_submit(h, s.x_stage, s.y_stage, &t) != 0) return -1;
+    if (dm_exec_submit(h, b, b + x_al, &t) != 0) { rc = -1; break; }
+    submitted.store(i + 1, std::memory_order_release);
     // harvest whatever has been retired so far (keeps stop latency at <= nslots steps)
     while (harvested < i + 1) {
       const uint64_t tk = first + harvested;
-      ExecSlot& hs = ex->slots[(tk - 1) % ex->slots.size()];
+      ExecSlot& hs = ex->slots[(tk - 1) % S];
       if (hs.in_flight && hs.ticket == tk) break;
       out[harvested] = ex->history[tk % kHistory];
       if (stop_at_global_step && out[harvested].global_step >= stop_at_global_step) stop = true;
       ++harvested;
     }
   }
+  quit.store(true, std::memory_order_relaxed);
+  gather.join();
+  if (rc != 0) return rc;
   if (dm_exec_drain(h) != 0) return -1;
   for (; harvested < i; ++harvested) out[harvested] = ex->history[(first + harvested) % kHistory];
   if (n_done) *n_done = i;
@@ -334,7 +417,9 @@ int dm_exec_destroy(void* h) {
     cudaEventDestroy(s.in_ready);
     cudaEventDestroy(s.done);
   }
-  cudaStreamDestroy(ex->compute);
+  for (uint8_t* b : ex->ring) cudaFreeHost(b);
+  for (cudaStream_t c : ex->compute) cudaStreamDestroy(c);
+  for (cudaEvent_t e : ex->lane_ev) cudaEventDestroy(e);
   cudaStreamDestroy(ex->copy);
   delete ex;
   return 0;

@@ -103,6 +103,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  grid_dep_launch();  // PDL: the next kernel of the step may set itself up while this one runs
   // optional phase timestamps (SM cycle counter) of CTA (0,0,0) — bench_tools/profile_kernels.py --phases
   long long* dbg = (p.debug_ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.debug_ts : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
@@ -123,8 +124,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
     // The first kernel of a training step opens a new push sequence number (it does not read it itself;
-    // every later kernel of the step does, after this kernel has completed).
-    if (p.bump_seq != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *p.bump_seq += 1;
+    // every later kernel of the step does, after this kernel has completed). Steps of different lanes may be
+    // in flight concurrently, hence the atomic draw from the worker-wide counter.
+    if (p.bump_seq != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+      *p.bump_seq = atomicAdd(p.seq_counter, 1u) + 1u;
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -141,6 +144,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  grid_dep_wait();    // PDL: everything above overlapped the previous kernel; its outputs are visible from here
   // Distributed shared memory of a peer CTA may only be touched once that CTA is known to be running:
   // everybody arrives here, and waits right before its first remote access / at the end of its role.
   if (cluster_mode) cluster_barrier_arrive_release();
@@ -563,23 +567,32 @@ static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, co
   const bool cluster = p.splitk_cluster != 0 && grid.z > 1;
   const size_t smem = gemm_smem_bytes(p.bn, p.stages, cluster ? 1 : 0);
   if (smem > static_cast<size_t>(kMaxDynSmem)) return cudaErrorInvalidValue;
-  if (!cluster) {
+  if (!cluster && !p.pdl) {
     kern<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p);
     return cudaGetLastError();
   }
-  if (grid.z > 8 || (2 * p.stages + 1) * sizeof(uint64_t) + 16 > 256) return cudaErrorInvalidValue;
+  if (cluster && (grid.z > 8 || (2 * p.stages + 1) * sizeof(uint64_t) + 16 > 256)) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;   // the K-splits of one output tile form a cluster
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = grid.z;
+  cudaLaunchAttribute attr[2];
+  unsigned na = 0;
+  if (cluster) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;   // the K-splits of one output tile form a cluster
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = grid.z;
+    ++na;
+  }
+  if (p.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
 }
 

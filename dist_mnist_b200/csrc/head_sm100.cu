@@ -101,6 +101,15 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
   __shared__ uint32_t s_gstep;
   long long* dbg = (p.debug_ts != nullptr && blockIdx.x == 0) ? p.debug_ts : nullptr;
   if (dbg && tid == 0) dbg[0] = clock64();
+  grid_dep_launch();  // PDL: the dW kernel may set itself up (barriers, TMEM, descriptors) while we run
+
+  // ---- phase A.1: stage W_last (peer loads from the PS shard) — independent of the forward kernels, so under
+  //      PDL it overlaps their tail ----
+  for (int i = tid; i < kMaxC * ldw; i += kHeadThreads) {
+    const int c = i / ldw, k = i - c * ldw;
+    sW[i] = (c < C && k < H) ? p.w_last[static_cast<size_t>(c) * H + k] : 0.f;
+  }
+  grid_dep_wait();    // the forward kernels' activations and the step's sequence number are visible from here
 
   if (tid == 0) {
     uint32_t seq = p.seq_ptr ? *reinterpret_cast<volatile uint32_t*>(p.seq_ptr) : 1u;
@@ -132,11 +141,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1) head_kernel(const __grid_cons
     if (dbg) dbg[1] = clock64();   // seq read + ack wait done
   }
 
-  // ---- phase A: stage W_last (peer loads from the PS shard) and this CTA's slice of h ----
-  for (int i = tid; i < kMaxC * ldw; i += kHeadThreads) {
-    const int c = i / ldw, k = i - c * ldw;
-    sW[i] = (c < C && k < H) ? p.w_last[static_cast<size_t>(c) * H + k] : 0.f;
-  }
+  // ---- phase A.2: this CTA's slice of h ----
   for (int i = tid; i < p.B_pad * kHeadSlice; i += kHeadThreads) {
     const int b = i / kHeadSlice, hh = i - b * kHeadSlice;
     sHs[i] = (b < B && h0 + hh < H) ? ld_act(p.h, static_cast<size_t>(b) * p.ldh + h0 + hh, p.act_bf16) : 0.f;
@@ -348,8 +353,21 @@ cudaError_t launch_head(const HeadParams& p, cudaStream_t stream) {
   const size_t smem = head_smem_bytes(p.B_pad, p.H, p.C);
   if (smem > static_cast<size_t>(kHeadMaxSmem)) return cudaErrorInvalidValue;
   const int grid = (p.H + kHeadSlice - 1) / kHeadSlice;
-  head_kernel<<<grid, kHeadThreads, smem, stream>>>(p);
-  return cudaGetLastError();
+  if (!p.pdl) {
+    head_kernel<<<grid, kHeadThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kHeadThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, head_kernel, p);
 }
 
 // ------------------------------------------------------------------------------------------

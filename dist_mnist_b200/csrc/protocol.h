@@ -68,12 +68,16 @@ struct GemmParams {
   uint64_t push_offset; // element offset of the variable inside push.base
   int push_item_base;   // first flag item index for this variable's tiles (tile = mtile * ntiles + ntile)
   int push_staged;      // 1: transpose the dW tile through smem so each warp store covers whole 256-byte row runs
-  uint32_t* bump_seq;   // if set, CTA (0,0,0) increments it: the first kernel of a step opens a new push seq
+  uint32_t* bump_seq;   // if set, CTA (0,0,0) opens a new push sequence number for this step: it draws
+  uint32_t* seq_counter;//   atomicAdd(seq_counter, 1) + 1 and stores it to *bump_seq (the step lane's seq word,
+                        //   which every later kernel of the same step reads through PushTarget::seq_ptr)
   float* splitk_scratch;     // gridDim.z > 1: [mtiles][splits][128][bn] fp32 partial tiles
   uint32_t* splitk_counter;  // gridDim.z > 1: [mtiles] arrival counters (self-resetting)
   long long* debug_ts;       // optional: 9 clock64() phase stamps of CTA (0,0,0); null in production
   int splitk_cluster;        // 1: the gridDim.z splits of a tile form one thread-block cluster and reduce
-  int pad2_;                 //    their partial accumulators through distributed shared memory
+  int pdl;                   //    their partial accumulators through distributed shared memory
+                             // pdl = 1: launch with programmatic stream serialization (prologue overlaps the
+                             //    previous kernel of the step; data reads wait on griddepcontrol.wait)
 };
 
 // Softmax-cross-entropy head (last dense layer + loss + its gradients), see head_sm100.cu
@@ -110,7 +114,7 @@ struct HeadParams {
   int item_w_last_base; // + blockIdx.x
   int item_b_last;
   int item_b_hidden_base;  // + blockIdx.x
-  int pad_;
+  int pdl;                 // 1: launch with programmatic stream serialization (see GemmParams::pdl)
   StepResult* result;      // device buffer (copied D2H by the step graph)
   // PS bookkeeping
   uint32_t* seq_ptr;         // local; bumped by the first kernel of the step (GemmParams::bump_seq), read here

@@ -150,7 +150,7 @@ def _base_params(M, N_, K, bn, dtype, splits) -> N.GemmParams:
 
 def forward_plan(*, w_ptr: int, x_ptr: int, out_ptr: int, bias_ptr: int, O: int, I: int, B: int, B_pad: int,
                  dtype: int, relu: bool, ldw: Optional[int] = None, ldx: Optional[int] = None,
-                 ldo: Optional[int] = None, bump_seq_ptr: int = 0, splits: Optional[int] = None,
+                 ldo: Optional[int] = None, bump_seq_ptr: int = 0, seq_counter_ptr: int = 0, splits: Optional[int] = None,
                  name: str = "fwd") -> GemmPlan:
     """out[b, o] = act(x[b, :] . W[o, :] + bias[o]); A = W (K-major, may be peer), B = x (K-major)."""
     assert B_pad % 16 == 0 and B_pad <= 256 and B <= B_pad
@@ -177,6 +177,7 @@ def forward_plan(*, w_ptr: int, x_ptr: int, out_ptr: int, bias_ptr: int, O: int,
     p.bias = bias_ptr
     p.relu = int(relu)
     p.bump_seq = bump_seq_ptr
+    p.seq_counter = seq_counter_ptr or bump_seq_ptr
     grid = (mtiles, 1, splits)
     plan = GemmPlan(tm_a, tm_b, p, dtype, False, False, splits, grid, name)
     _attach_splitk(plan, mtiles, splits, B_pad)

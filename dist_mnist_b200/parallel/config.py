@@ -1,9 +1,18 @@
 """Engine configuration shared by ps and worker tasks."""
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, asdict
 
 from .. import _native as N
+
+
+MAX_LANES = 4
+
+
+def _env_flag(name: str, default: bool) -> bool:
+    v = os.environ.get(name)
+    return default if v is None else v not in ("0", "", "false", "False")
 
 
 @dataclass(frozen=True)
@@ -36,6 +45,10 @@ class EngineConfig:
     ps_ctas: int = 0                 # CTAs of the persistent PS kernel (0 = auto: 120 on a dedicated ps GPU,
                                      # 32 when a worker shares the GPU)
     pipeline_slots: int = 4          # worker executor ring depth
+    lanes: int = 1                   # steps of one worker in flight on the GPU at once (compute streams). 1 = each
+                                     # step starts after the previous one's kernels (reference-like); 2 = step i+1's
+                                     # pull/forward overlaps step i's backward/push (needs nslots >= lanes)
+    pdl: bool = _env_flag("DM_PDL", False)  # programmatic dependent launch between the kernels of a step graph
     colocate: bool = False           # worker i shares GPU i with ps i (N workers on N GPUs)
 
     @property
@@ -68,6 +81,12 @@ class EngineConfig:
                 raise ValueError("push_mode='atomic' needs the cuda backend")
         if self.nslots < 1:
             raise ValueError("nslots must be >= 1")
+        if self.lanes < 1 or self.lanes > MAX_LANES:
+            raise ValueError(f"lanes must be in [1, {MAX_LANES}]")
+        if self.push_mode == "mailbox" and self.lanes > self.nslots:
+            raise ValueError("lanes (steps in flight) cannot exceed nslots (mailbox slots per worker)")
+        if self.pipeline_slots % self.lanes != 0:
+            raise ValueError("pipeline_slots must be a multiple of lanes")
         _ = self.native_dtype, self.native_apply_mode, opt.native_kind
 
     def as_dict(self) -> dict:

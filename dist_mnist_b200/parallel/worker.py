@@ -31,7 +31,7 @@ from ..models import mlp
 from ..models.mlp import MLPSpec
 from ..ops import gemm as gemm_ops
 from ..ops import head as head_ops
-from .config import EngineConfig, OptimizerConfig
+from .config import MAX_LANES, EngineConfig, OptimizerConfig
 from .peer_mem import Carver, Segment
 from .ps import CTRL_GLOBAL_STEP, CTRL_WORKER_DONE
 from .sharding import ModelLayout, VarLayout, build_layout
@@ -105,7 +105,7 @@ class Worker:
             self.ps_segs.append(Segment.open(desc, device=self.device))
         carver = Carver()
         carver.add("inbox", max(1, len(self.inbox_order)) * 8)
-        carver.add("seq", 4)
+        carver.add("seq", 4 * (1 + MAX_LANES))   # [0] pushes opened so far, [1 + lane] seq of the lane's current step
         kind = "cuda" if cfg.backend == "cuda" else "shm"
         self.seg = Segment.create(kind, carver.total, device=self.device, table=carver.table(),
                                   tag=f"w{self.task_index}")
@@ -256,7 +256,7 @@ class Worker:
     # ------------------------------------------------------------------------------------------
     # GPU step construction
     # ------------------------------------------------------------------------------------------
-    def _push_target(self, k: int) -> N.PushTarget:
+    def _push_target(self, k: int, seq_ptr: int) -> N.PushTarget:
         seg, desc = self.ps_segs[k], self.ps_desc[k]
         t = N.PushTarget()
         w = self.task_index
@@ -271,7 +271,7 @@ class Worker:
             t.flags = seg.addr("flags", w * ns * ni * 4)
             t.flag_slot_stride = ni
             t.nslots = ns
-        t.seq_ptr = self.seg.addr("seq")
+        t.seq_ptr = seq_ptr
         # ps shard on our own GPU (in-process / colocated): gpu-scope release suffices for its flags
         t.gpu_scope = int(self.cfg.backend == "cuda" and desc.get("device", -2) == self.device
                           and self.cluster.num_workers == 1)
@@ -289,7 +289,8 @@ class Worker:
         x_bytes = self.B_pad * self.ld_in * self.es
         y_bytes = self.B_pad * spec.num_classes * 4
         out = C.c_void_p()
-        N.check(self.lib.dm_exec_create(self.device, cfg.pipeline_slots, x_bytes, y_bytes, C.byref(out)), "exec create")
+        N.check(self.lib.dm_exec_create(self.device, cfg.pipeline_slots, cfg.lanes, x_bytes, y_bytes, C.byref(out)),
+                "exec create")
         self._exec = out.value
         self.x_bytes, self.y_bytes = x_bytes, y_bytes
         dev = f"cuda:{self.device}"
@@ -297,10 +298,12 @@ class Worker:
         sizes = spec.layer_sizes
         L = len(sizes)
         # activations / pre-activation gradients of the hidden layers (row padded, zero initialised)
-        self.act = [None] + [torch.zeros(self.B_pad, gemm_ops.padded_ld(sizes[l][1]), dtype=self.tdtype, device=dev)
-                             for l in range(L - 1)]
-        self.dact = [None] + [torch.zeros_like(self.act[l + 1]) for l in range(L - 1)]
-        seq_ptr = self.seg.addr("seq")
+        # (one set per lane: steps of different lanes run concurrently)
+        self._lane_act = [[None] + [torch.zeros(self.B_pad, gemm_ops.padded_ld(sizes[l][1]), dtype=self.tdtype,
+                                                device=dev) for l in range(L - 1)] for _ in range(cfg.lanes)]
+        self._lane_dact = [[None] + [torch.zeros_like(a[l + 1]) for l in range(L - 1)] for a in self._lane_act]
+        self.act, self.dact = self._lane_act[0], self._lane_dact[0]
+        seq_counter = self.seg.addr("seq")
         self._slots = []
         stream = self.lib.dm_exec_compute_stream(self._exec)
         # ---- evaluation path (forward + head without gradients; shares the activation buffers) ----
@@ -326,6 +329,10 @@ class Worker:
             act_bf16=cfg.dtype == "bf16", compute_grads=False, ldh=self.act[L - 1].shape[1]))
         torch.cuda.synchronize(self.device)
         for slot in range(cfg.pipeline_slots):
+            lane = slot % cfg.lanes
+            act, dact = self._lane_act[lane], self._lane_dact[lane]
+            seq_ptr = self.seg.addr("seq", 4 * (1 + lane))
+            stream = self.lib.dm_exec_lane_stream(self._exec, lane)
             xd, yd, rd, xs, ys = (C.c_void_p() for _ in range(5))
             N.check(self.lib.dm_exec_slot_info(self._exec, slot, C.byref(xd), C.byref(yd), C.byref(rd), C.byref(xs),
                                                C.byref(ys)))
@@ -335,13 +342,13 @@ class Worker:
                 wn, bn = names[l]
                 wl, bl = lay.by_name[wn], lay.by_name[bn]
                 fin, fout = sizes[l]
-                in_ptr = xd.value if l == 0 else self.act[l].data_ptr()
-                ld_in = self.ld_in if l == 0 else self.act[l].shape[1]
+                in_ptr = xd.value if l == 0 else act[l].data_ptr()
+                ld_in = self.ld_in if l == 0 else act[l].shape[1]
                 plans.append(gemm_ops.forward_plan(
-                    w_ptr=self._weight_ptr(wl), x_ptr=in_ptr, out_ptr=self.act[l + 1].data_ptr(),
+                    w_ptr=self._weight_ptr(wl), x_ptr=in_ptr, out_ptr=act[l + 1].data_ptr(),
                     bias_ptr=self.ps_segs[bl.ps].addr("params", bl.offset * 4), O=fout, I=fin, B=self.batch,
-                    B_pad=self.B_pad, dtype=self.dt, relu=True, ldw=wl.ld, ldx=ld_in, ldo=self.act[l + 1].shape[1],
-                    bump_seq_ptr=seq_ptr if l == 0 else 0, name=f"fwd{l}"))
+                    B_pad=self.B_pad, dtype=self.dt, relu=True, ldw=wl.ld, ldx=ld_in, ldo=act[l + 1].shape[1],
+                    bump_seq_ptr=seq_ptr if l == 0 else 0, seq_counter_ptr=seq_counter, name=f"fwd{l}"))
             # ---- classifier head ----
             wn, bn = names[L - 1]
             wl, bl = lay.by_name[wn], lay.by_name[bn]
@@ -349,36 +356,43 @@ class Worker:
             inbox_ptr = self.seg.addr("inbox") if cfg.push_mode == "mailbox" else 0
             gs_ptr = self.ps_segs[self.gs_owner].addr("ctrl", 4 * CTRL_GLOBAL_STEP) if cfg.push_mode == "atomic" else 0
             plans.append(head_ops.head_plan(
-                h_ptr=self.act[L - 1].data_ptr(), labels_ptr=yd.value,
+                h_ptr=act[L - 1].data_ptr(), labels_ptr=yd.value,
                 w_last_ptr=self.ps_segs[wl.ps].addr("params", wl.offset * 4),
                 b_last_ptr=self.ps_segs[bl.ps].addr("params", bl.offset * 4),
-                dpre_ptr=self.dact[L - 1].data_ptr(), result_ptr=rd.value, B=self.batch, B_pad=self.B_pad,
+                dpre_ptr=dact[L - 1].data_ptr(), result_ptr=rd.value, B=self.batch, B_pad=self.B_pad,
                 H=sizes[L - 1][0], num_classes=spec.num_classes,
                 loss_kind=N.LOSS_BOOK if spec.loss == "book" else N.LOSS_XENT, act_bf16=cfg.dtype == "bf16",
-                push=self._push_target(wl.ps), push_bh=self._push_target(hb.ps), push_bl=self._push_target(bl.ps),
+                push=self._push_target(wl.ps, seq_ptr), push_bh=self._push_target(hb.ps, seq_ptr),
+                push_bl=self._push_target(bl.ps, seq_ptr),
                 off_w_last=wl.offset, off_b_last=bl.offset, off_b_hidden=hb.offset,
                 item_w_last_base=wl.item_base, item_b_last=bl.item_base, item_b_hidden_base=hb.item_base,
                 seq_ptr=seq_ptr, inbox_ptr=inbox_ptr, n_inbox=len(self.inbox_order), ps_global_step_ptr=gs_ptr,
-                nslots=cfg.nslots, ldh=self.act[L - 1].shape[1]))
+                nslots=cfg.nslots, ldh=act[L - 1].shape[1]))
             # ---- backward: dW (fused push) and dX (+ bias-grad push) of the hidden layers ----
             for l in range(L - 2, -1, -1):
                 wn, bn = names[l]
                 wl = lay.by_name[wn]
                 fin, fout = sizes[l]
-                in_ptr = xd.value if l == 0 else self.act[l].data_ptr()
-                ld_in = self.ld_in if l == 0 else self.act[l].shape[1]
+                in_ptr = xd.value if l == 0 else act[l].data_ptr()
+                ld_in = self.ld_in if l == 0 else act[l].shape[1]
                 plans.append(gemm_ops.dw_plan(
-                    dy_ptr=self.dact[l + 1].data_ptr(), x_ptr=in_ptr, O=fout, I=fin, B_pad=self.B_pad, dtype=self.dt,
-                    push=self._push_target(wl.ps), push_offset=wl.offset, item_base=wl.item_base,
-                    lddy=self.dact[l + 1].shape[1], ldx=ld_in, ldw=wl.ld, name=f"dw{l}"))
+                    dy_ptr=dact[l + 1].data_ptr(), x_ptr=in_ptr, O=fout, I=fin, B_pad=self.B_pad, dtype=self.dt,
+                    push=self._push_target(wl.ps, seq_ptr), push_offset=wl.offset, item_base=wl.item_base,
+                    lddy=dact[l + 1].shape[1], ldx=ld_in, ldw=wl.ld, name=f"dw{l}"))
                 if l > 0:
                     pb = lay.by_name[names[l - 1][1]]  # bias of the previous hidden layer gets its grad here
                     plans.append(gemm_ops.dx_plan(
-                        w_ptr=self._weight_ptr(wl), dy_ptr=self.dact[l + 1].data_ptr(), out_ptr=self.dact[l].data_ptr(),
-                        mask_ptr=self.act[l].data_ptr(), O=fout, I=fin, B=self.batch, B_pad=self.B_pad, dtype=self.dt,
-                        ldw=wl.ld, lddy=self.dact[l + 1].shape[1], ldo=self.dact[l].shape[1],
-                        colsum=self._push_target(pb.ps), colsum_offset=pb.offset, colsum_item_base=pb.item_base,
+                        w_ptr=self._weight_ptr(wl), dy_ptr=dact[l + 1].data_ptr(), out_ptr=dact[l].data_ptr(),
+                        mask_ptr=act[l].data_ptr(), O=fout, I=fin, B=self.batch, B_pad=self.B_pad, dtype=self.dt,
+                        ldw=wl.ld, lddy=dact[l + 1].shape[1], ldo=dact[l].shape[1],
+                        colsum=self._push_target(pb.ps, seq_ptr), colsum_offset=pb.offset, colsum_item_base=pb.item_base,
                         name=f"dx{l}"))
+            if cfg.pdl:
+                # programmatic dependent launch inside the step graph: kernel k+1's prologue (and the head's
+                # W_last fetch) overlaps kernel k; every kernel waits on griddepcontrol.wait before it touches
+                # its predecessor's outputs. The first kernel keeps a full dependency on the previous step.
+                for p in plans[1:]:
+                    p.params.pdl = 1
             self.kernels_per_step = len(plans)
             N.check(self.lib.dm_exec_begin_capture(self._exec, slot), "begin capture")
             try:
@@ -476,9 +490,17 @@ class Worker:
     def enqueue_wait_ack(self) -> None:
         """Stream-ordered fence: the compute stream does not proceed until the PS has applied every push made so
         far (mailbox mode). Used to close a device-timed region on the PS-side apply of its last step."""
-        if self.cfg.backend == "cuda" and self.cfg.push_mode == "mailbox" and self.inbox_order:
+        if self.cfg.backend != "cuda":
+            return
+        N.check(self.lib.dm_exec_join(self._exec), "join lanes")   # lane 0 now follows every in-flight step
+        if self.cfg.push_mode == "mailbox" and self.inbox_order:
             N.check(self.lib.dm_launch_wait_ack(self.seg.addr("inbox"), len(self.inbox_order), self.seg.addr("seq"),
                                                 self.compute_stream), "wait_ack")
+
+    def fork_lanes(self) -> None:
+        """Every lane waits for what is enqueued on lane 0 (e.g. a timing event) before running further steps."""
+        if self.cfg.backend == "cuda" and self._exec:
+            N.check(self.lib.dm_exec_fork(self._exec), "fork lanes")
 
     def kernel_launches(self) -> int:
         return int(self.lib.dm_exec_kernel_launches(self._exec)) if self._exec else 0
