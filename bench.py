@@ -52,9 +52,11 @@ def parse_args(argv=None):
     p.add_argument("--apply_mode", choices=["per_push", "merged"], default="per_push")
     p.add_argument("--num_ps", type=int, default=1)
     p.add_argument("--sharding", choices=["round_robin", "byte_balanced"], default="round_robin")
-    p.add_argument("--nslots", type=int, default=2)
-    p.add_argument("--lanes", type=int, default=2,
+    p.add_argument("--nslots", type=int, default=0, help="mailbox slots per worker (0 = max(2, lanes))")
+    p.add_argument("--lanes", type=int, default=8,
                    help="steps of one worker in flight on its GPU at once (async SGD; must be <= nslots)")
+    p.add_argument("--graph_steps", type=int, default=0,
+                   help="steps per CUDA-graph launch in the native loops (0 = min(lanes, 4))")
     p.add_argument("--skip_e2e", action="store_true")
     return p.parse_args(argv)
 
@@ -96,9 +98,11 @@ def main(argv=None) -> int:
 
     spec = mlp.get_model(args.model, args.hidden_units)
     opt = OptimizerConfig(args.optimizer, args.learning_rate)
+    args.nslots = args.nslots or max(2, args.lanes)
+    args.graph_steps = args.graph_steps or min(args.lanes, 4)
     cfg = EngineConfig(backend="cuda", dtype=args.dtype, nslots=args.nslots, apply_mode=args.apply_mode,
                        push_mode=args.push_mode, sharding=args.sharding, lanes=args.lanes,
-                       pipeline_slots=max(4, 2 * args.lanes))
+                       graph_steps=args.graph_steps, pipeline_slots=max(4, 2 * args.lanes))
     cfg.validate(opt)
     K, W, B = args.steps, args.warmup, args.batch_size
 
@@ -283,6 +287,8 @@ def main(argv=None) -> int:
                 "optimizer": f"{args.optimizer} lr={args.learning_rate}",
                 "apply": f"{args.push_mode}/{args.apply_mode}",
                 "steps_in_flight_per_worker": args.lanes,
+                "steps_per_graph_launch": args.graph_steps,
+                "mailbox_slots": args.nslots,
                 "host_enqueue_us_per_step": round(float(mx[7]) * 1e3 / K, 2),
                 "l2_policy": "inputs stream from a 55000x784 device-resident dataset (172 MB fp32 > 126 MB L2); "
                              "parameters (0.3 MB) stay L2-resident as in real training",

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import subprocess
 import sys
+import os
 import time
 import traceback
 
@@ -82,11 +83,18 @@ def check_traj(only=None) -> bool:
                 for i in range(n_steps):
                     x, y = it.next_batch(batch)
                     r = w.step(x, y)
+                    if os.environ.get("DM_TRAJ_WAIT", "applied") == "applied":
+                        w.wait_applied()   # every shard has applied the push (global_step lives on shard 0 only)
                     wait_gstep(w, i + 1)
                     lref, t = ref_step(spec, ref_p, ref_m, ref_v, t, x, y, opt)
                     worst = max(worst, abs(r.loss - lref) / (abs(lref) + 1e-9))
+                    if os.environ.get("DM_TRAJ_VERBOSE"):
+                        print(f"      step {i}: loss {r.loss!r} ref {lref!r}", flush=True)
                 got = w.read_variables()
-                perr = max(float((got[k] - ref_p[k]).norm() / (ref_p[k].norm() + 1e-9)) for k in got)
+                perrs = {k: float((got[k] - ref_p[k]).norm() / (ref_p[k].norm() + 1e-9)) for k in got}
+                perr = max(perrs.values())
+                if os.environ.get("DM_TRAJ_VERBOSE"):
+                    print("    per-variable rel err: " + " ".join(f"{k}={v:.2e}" for k, v in perrs.items()), flush=True)
                 gs = w.read_global_step()
                 acc_loss, acc = w.evaluate(ds.images[:512], ds.labels[:512])
             good = worst < tol and perr < tol and gs == n_steps
@@ -137,7 +145,53 @@ def check_throughput(only=None) -> bool:
     return ok
 
 
-CHECKS = {"traj": check_traj, "throughput": check_throughput}
+PIPE_CASES = [("book", "adam", "fp32", "mailbox", 2, 1, False), ("book", "adam", "fp32", "mailbox", 4, 2, True),
+              ("book", "sgd", "fp32", "atomic", 4, 4, True), ("wide", "adam", "bf16", "mailbox", 4, 2, True),
+              ("zhihu", "sgd", "fp32", "mailbox", 2, 2, False)]
+
+
+def check_pipelined(only=None) -> bool:
+    """Several steps in flight (lanes) and several steps per graph launch (graph_steps): every step gets a unique
+    push sequence number, every push is applied exactly once (global_step == steps), results come back in
+    submission order and training still converges; mixes odd-sized runs so that the single-step head / tail paths
+    of the native loop are exercised next to the group launches."""
+    ok = True
+    ds = data.synthetic_mnist(8192, seed=0)
+    for (model, okind, dtype, push, lanes, gsteps, pdl) in (PIPE_CASES if only is None else [PIPE_CASES[only]]):
+        name = f"pipelined model={model} opt={okind} dtype={dtype} push={push} lanes={lanes} graph_steps={gsteps} pdl={pdl}"
+        try:
+            spec = mlp.get_model(model)
+            opt = OptimizerConfig(okind, 1e-3 if okind == "adam" else 1e-2)
+            cfg = EngineConfig(backend="cuda", dtype=dtype, push_mode=push, lanes=lanes, graph_steps=gsteps,
+                               nslots=max(2, lanes), pipeline_slots=max(4, 2 * lanes), pdl=pdl)
+            with InProcessCluster(spec, opt, cfg, batch_size=32) as cl:
+                w = cl.worker
+                loader = w.make_loader(ds.images, ds.labels, seed=0)
+                outs = []
+                for n in (3, 301, 1, 200, 7):
+                    outs += w.run_steps(n, loader)
+                x, y = loader.next_batch()
+                outs.append(w.step(x, y))          # synchronous API on the same executor
+                outs += w.run_steps(88, loader)
+                total = 3 + 301 + 1 + 200 + 7 + 1 + 88
+                w.wait_applied()
+                gs = w.read_global_step()
+                seqs = sorted(o.seq for o in outs)
+                first = sum(o.loss for o in outs[:20]) / 20
+                last = sum(o.loss for o in outs[-20:]) / 20
+                good = (len(outs) == total and gs == total and seqs == list(range(1, total + 1))
+                        and last < first and all(o.loss == o.loss for o in outs))
+                print(f"[{'PASS' if good else 'FAIL'}] {name}: steps={len(outs)} global_step={gs} "
+                      f"seqs unique={seqs == list(range(1, total + 1))} loss {first:.4f} -> {last:.4f}", flush=True)
+                ok &= good
+        except Exception:
+            traceback.print_exc()
+            print(f"[FAIL] {name}: exception", flush=True)
+            ok = False
+    return ok
+
+
+CHECKS = {"traj": check_traj, "throughput": check_throughput, "pipelined": check_pipelined}
 
 
 def main(argv) -> int:

@@ -109,16 +109,16 @@ def main() -> int:
     for l in range(L - 2, -1, -1):
         wl = lay.by_name[names[l][0]]
         fin, fout = sizes[l]
-        plans.append(gemm.dw_plan(dy_ptr=dact[l + 1].data_ptr(), x_ptr=x.data_ptr() if l == 0 else act[l].data_ptr(),
-                                  O=fout, I=fin, B_pad=B_pad, dtype=dt, push=push, push_offset=wl.offset,
-                                  item_base=wl.item_base, lddy=dact[l + 1].shape[1],
-                                  ldx=ld_in if l == 0 else act[l].shape[1], ldw=wl.ld, name=f"dw{l}"))
-        if l > 0:
+        if l > 0:   # dX before dW of the same layer (see Worker._build_cuda)
             pb = lay.by_name[names[l - 1][1]]
             plans.append(gemm.dx_plan(w_ptr=wptr(wl), dy_ptr=dact[l + 1].data_ptr(), out_ptr=dact[l].data_ptr(),
                                       mask_ptr=act[l].data_ptr(), O=fout, I=fin, B=B, B_pad=B_pad, dtype=dt,
                                       ldw=wl.ld, lddy=dact[l + 1].shape[1], ldo=dact[l].shape[1], colsum=push,
                                       colsum_offset=pb.offset, colsum_item_base=pb.item_base, name=f"dx{l}"))
+        plans.append(gemm.dw_plan(dy_ptr=dact[l + 1].data_ptr(), x_ptr=x.data_ptr() if l == 0 else act[l].data_ptr(),
+                                  O=fout, I=fin, B_pad=B_pad, dtype=dt, push=push, push_offset=wl.offset,
+                                  item_base=wl.item_base, lddy=dact[l + 1].shape[1],
+                                  ldx=ld_in if l == 0 else act[l].shape[1], ldw=wl.ld, name=f"dw{l}"))
 
     if args.pdl:
         for p_ in plans[1:]:

@@ -104,7 +104,7 @@ class PsServeParams(C.Structure):
         ("global_step", C.c_void_p), ("worker_done", C.c_void_p), ("host_stop", C.c_void_p),
         ("inbox_table", C.c_void_p),
         ("exit_counter", C.c_void_p),
-        ("gpu_scope", C.c_uint32), ("pad_", C.c_uint32),
+        ("gpu_scope", C.c_uint32), ("lookahead", C.c_uint32),
     ]
 
 
@@ -184,9 +184,12 @@ def _declare(l: C.CDLL) -> None:
         "dm_loader_next": (None, [vp, vp, vp]),
         "dm_loader_epochs": (u64, [vp]),
         "dm_loader_destroy": (None, [vp]),
-        "dm_exec_create": (i, [i, i, i, sz, sz, C.POINTER(vp)]),
-        "dm_exec_lane_stream": (vp, [vp, i]),
-        "dm_exec_lanes": (i, [vp]),
+        "dm_exec_create": (i, [i, i, i, i, sz, sz, C.POINTER(vp)]),
+        "dm_exec_capture_stream": (vp, [vp, i]),
+        "dm_exec_graph_steps": (i, [vp]),
+        "dm_exec_begin_group_capture": (i, [vp, i]),
+        "dm_exec_end_group_capture": (i, [vp, i]),
+        "dm_exec_submit_group": (i, [vp, vp, vp, sz, vp, sz, C.POINTER(u64)]),
         "dm_exec_join": (i, [vp]),
         "dm_exec_fork": (i, [vp]),
         "dm_exec_slot_info": (i, [vp, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
@@ -216,6 +219,9 @@ def lib(build_if_missing: bool = True) -> C.CDLL:
     if _lib is not None:
         return _lib
     path = lib_path()
+    if os.environ.get("DM_NATIVE_LIB"):     # debugging aid: load an alternative build of the library (A/B runs)
+        path = Path(os.environ["DM_NATIVE_LIB"])
+        os.environ["DM_NO_BUILD"] = "1"
     if os.environ.get("DM_NO_BUILD") != "1":
         if not build_if_missing and not path.exists():
             raise NativeError(f"native library {path} is missing; run `python -m dist_mnist_b200._build`")

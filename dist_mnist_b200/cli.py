@@ -63,6 +63,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--lanes", type=int, default=1,
                    help="steps of this worker in flight at once (1 = like the reference: a step starts after the "
                         "previous one's kernels; 2 overlaps consecutive steps, needs --nslots >= 2)")
+    p.add_argument("--graph_steps", type=int, default=1,
+                   help="steps per CUDA-graph launch in the native train loop (divides --lanes)")
     p.add_argument("--checkpoint_dir", type=str, default=None, help="chief checkpoints here (default: mkdtemp, DS:106)")
     p.add_argument("--save_checkpoint_secs", type=float, default=600.0)
     p.add_argument("--gpu", type=int, default=None, help="CUDA device for this task (default: ps k -> k, worker i -> num_ps+i)")
@@ -105,7 +107,8 @@ def run(args: argparse.Namespace) -> int:
     spec = mlp.get_model(args.model, args.hidden_units)
     opt = OptimizerConfig(args.optimizer, args.learning_rate)
     cfg = EngineConfig(backend=backend, dtype=args.dtype, nslots=args.nslots, apply_mode=args.apply_mode,
-                       push_mode=args.push_mode, sharding=args.sharding, colocate=args.colocate, lanes=args.lanes)
+                       push_mode=args.push_mode, sharding=args.sharding, colocate=args.colocate, lanes=args.lanes,
+                       graph_steps=args.graph_steps, pipeline_slots=max(4, 2 * args.lanes))
     cfg.validate(opt)
     device = -1
     if backend == "cuda":

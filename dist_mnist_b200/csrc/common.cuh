@@ -234,6 +234,18 @@ __device__ __forceinline__ uint32_t atom_add_sys_u32(uint32_t* p, uint32_t v) {
   asm volatile("atom.add.relaxed.sys.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
   return old;
 }
+// Monotone publication of a counter into (possibly peer) memory: several CTAs may acknowledge consecutive
+// pushes of one worker at almost the same time, and a plain store of the older value landing last would move
+// the acknowledged sequence number backwards. `release` orders the publisher's earlier writes before it.
+__device__ __forceinline__ void red_max_release_scoped_u32(uint32_t* p, uint32_t v, uint32_t gpu_scope) {
+  if (gpu_scope) asm volatile("red.release.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+  else asm volatile("red.release.sys.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_max_relaxed_scoped_u32(uint32_t* p, uint32_t v, uint32_t gpu_scope) {
+  if (gpu_scope) asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+  else asm volatile("red.relaxed.sys.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // Fire-and-forget fp32 reduction into (possibly peer) global memory: the SGD "push == apply" path.
 __device__ __forceinline__ void red_add_sys_f32(float* p, float v) {
   asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");

@@ -172,7 +172,7 @@ struct PsServeParams {
   uint32_t* volatile* inbox_table;
   uint32_t* exit_counter;      // CTAs increment on exit (debug / clean shutdown)
   uint32_t gpu_scope;          // 1: every worker runs on the PS's own GPU (flags / acks at gpu scope)
-  uint32_t pad_;
+  uint32_t lookahead;          // max pushes of one worker consumed per item pass (0 = auto: up to nslots)
 };
 
 }  // namespace dm

@@ -16,12 +16,9 @@
 
 namespace dm {
 
-constexpr int kPsThreads = 256;
-
-struct UpdateCtx {
-  int opt;
-  float lr, beta1, beta2, eps;
-};
+constexpr int kPsThreads = 512;
+constexpr int kMaxOwn = 32;   // items one CTA may own (their descriptors / state / cursors live in shared memory)
+constexpr int kQuads = 2;     // element quads per thread per pass: all their loads are in flight together
 
 __device__ __forceinline__ void adam_step(float& p, float& m, float& v, float g, float lr_t, float beta1,
                                           float beta2, float eps) {
@@ -31,163 +28,244 @@ __device__ __forceinline__ void adam_step(float& p, float& m, float& v, float g,
   p -= lr_t * m / (sqrtf(v) + eps);
 }
 
-// Apply the gradients of the ready workers (bitmask) to one item. Called by the whole CTA.
-__device__ void apply_item(const PsServeParams& P, const PsItem it, PsItemState st, uint32_t mask,
-                           const uint32_t* s_seq) {
+// Apply every ready push to one item: worker w contributes its pushes s_seq[w] .. s_seq[w] + s_cnt[w] - 1 (their
+// mailbox slots are all flagged), applied one optimizer step per push in that order (or summed into a single
+// step in APPLY_MERGED mode) while the parameters and Adam slots stay in registers. Called by the whole CTA.
+__device__ void apply_item(const PsServeParams& P, const PsItem it, const PsItemState st, const uint32_t* s_seq,
+                           const uint32_t* s_cnt, const uint32_t kmax) {
   const int tid = threadIdx.x;
   const uint64_t wstride = static_cast<uint64_t>(P.nslots) * P.arena_elems;
-  // per-push schedule of lr_t (same for every element of the item)
   const int total = it.rows * it.cols;
   const bool vec = ((it.cols & 3) == 0) && ((it.ld & 3) == 0) && ((it.offset & 3) == 0);
   const int step = vec ? 4 : 1;
-  for (int e = tid * step; e < total; e += kPsThreads * step) {
-    const int r = e / it.cols;
-    const int c = e - r * it.cols;
-    const uint64_t a = it.offset + static_cast<uint64_t>(r) * it.ld + c;
-    float pv[4], mv[4] = {0, 0, 0, 0}, vv[4] = {0, 0, 0, 0};
-    if (vec) {
-      const float4 t = *reinterpret_cast<const float4*>(P.params + a);
-      pv[0] = t.x; pv[1] = t.y; pv[2] = t.z; pv[3] = t.w;
-      if (P.opt == OPT_ADAM) {
-        const float4 tm = *reinterpret_cast<const float4*>(P.adam_m + a);
-        const float4 tv = *reinterpret_cast<const float4*>(P.adam_v + a);
-        mv[0] = tm.x; mv[1] = tm.y; mv[2] = tm.z; mv[3] = tm.w;
-        vv[0] = tv.x; vv[1] = tv.y; vv[2] = tv.z; vv[3] = tv.w;
+  const bool adam = P.opt == OPT_ADAM;
+  for (int e0 = tid * step; e0 < total; e0 += kPsThreads * step * kQuads) {
+    uint64_t a[kQuads];
+    bool ok[kQuads];
+    float pv[kQuads][4], mv[kQuads][4], vv[kQuads][4], gsum[kQuads][4];
+#pragma unroll
+    for (int q = 0; q < kQuads; ++q) {
+      const int e = e0 + q * kPsThreads * step;
+      ok[q] = e < total;
+      const int r = ok[q] ? e / it.cols : 0;
+      const int c = ok[q] ? e - r * it.cols : 0;
+      a[q] = it.offset + static_cast<uint64_t>(r) * it.ld + c;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { pv[q][j] = 0.f; mv[q][j] = 0.f; vv[q][j] = 0.f; gsum[q][j] = 0.f; }
+    }
+#pragma unroll
+    for (int q = 0; q < kQuads; ++q) {
+      if (!ok[q]) continue;
+      if (vec) {
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(P.params + a[q]));
+        pv[q][0] = t.x; pv[q][1] = t.y; pv[q][2] = t.z; pv[q][3] = t.w;
+        if (adam) {
+          const float4 tm = __ldcg(reinterpret_cast<const float4*>(P.adam_m + a[q]));
+          const float4 tv = __ldcg(reinterpret_cast<const float4*>(P.adam_v + a[q]));
+          mv[q][0] = tm.x; mv[q][1] = tm.y; mv[q][2] = tm.z; mv[q][3] = tm.w;
+          vv[q][0] = tv.x; vv[q][1] = tv.y; vv[q][2] = tv.z; vv[q][3] = tv.w;
+        }
+      } else {
+        pv[q][0] = __ldcg(P.params + a[q]);
+        if (adam) { mv[q][0] = __ldcg(P.adam_m + a[q]); vv[q][0] = __ldcg(P.adam_v + a[q]); }
       }
-    } else {
-      pv[0] = P.params[a];
-      if (P.opt == OPT_ADAM) { mv[0] = P.adam_m[a]; vv[0] = P.adam_v[a]; }
     }
     float b1p = st.beta1_pow, b2p = st.beta2_pow;
-    float gsum[4] = {0, 0, 0, 0};
-    uint32_t mm = mask;
-    while (mm) {
-      const int w = __ffs(mm) - 1;
-      mm &= mm - 1;
-      const uint32_t slot = s_seq[w] % P.nslots;
-      const float* gsrc = P.mailbox + static_cast<uint64_t>(w) * wstride + static_cast<uint64_t>(slot) * P.arena_elems + a;
-      float g[4];
-      if (vec) {
-        const float4 t = __ldcg(reinterpret_cast<const float4*>(gsrc));  // L2 only: written remotely over NVLink
-        g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
-      } else {
-        g[0] = __ldcg(gsrc);
+    // round k takes the k-th pending push of every worker (oldest first, workers interleaved). APPLY_MERGED
+    // sums the pushes of one round (concurrent pushes of different workers) into a single optimizer step;
+    // consecutive pushes of the same worker always stay separate steps.
+    for (uint32_t k = 0; k < kmax; ++k) {
+      for (int w = 0; w < P.n_workers; ++w) {
+        if (k >= s_cnt[w]) continue;
+        const uint32_t slot = (s_seq[w] + k) % P.nslots;
+        const float* gbase = P.mailbox + static_cast<uint64_t>(w) * wstride + static_cast<uint64_t>(slot) * P.arena_elems;
+        float g[kQuads][4];
+#pragma unroll
+        for (int q = 0; q < kQuads; ++q) {
+          g[q][0] = g[q][1] = g[q][2] = g[q][3] = 0.f;
+          if (!ok[q]) continue;
+          if (vec) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(gbase + a[q]));  // L2: written over NVLink
+            g[q][0] = t.x; g[q][1] = t.y; g[q][2] = t.z; g[q][3] = t.w;
+          } else {
+            g[q][0] = __ldcg(gbase + a[q]);
+          }
+        }
+        if (P.apply_mode == APPLY_MERGED) {
+#pragma unroll
+          for (int q = 0; q < kQuads; ++q)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gsum[q][j] += g[q][j];
+          continue;
+        }
+        if (adam) {
+          b1p *= P.beta1;
+          b2p *= P.beta2;
+          const float lr_t = P.lr * sqrtf(1.f - b2p) / (1.f - b1p);
+#pragma unroll
+          for (int q = 0; q < kQuads; ++q)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < step) adam_step(pv[q][j], mv[q][j], vv[q][j], g[q][j], lr_t, P.beta1, P.beta2, P.eps);
+        } else {
+#pragma unroll
+          for (int q = 0; q < kQuads; ++q)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < step) pv[q][j] = fmaf(-P.lr, g[q][j], pv[q][j]);
+        }
       }
       if (P.apply_mode == APPLY_MERGED) {
+        if (adam) {
+          b1p *= P.beta1;
+          b2p *= P.beta2;
+          const float lr_t = P.lr * sqrtf(1.f - b2p) / (1.f - b1p);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) gsum[j] += g[j];
-        continue;
-      }
-      if (P.opt == OPT_ADAM) {
-        b1p *= P.beta1;
-        b2p *= P.beta2;
-        const float lr_t = P.lr * sqrtf(1.f - b2p) / (1.f - b1p);
+          for (int q = 0; q < kQuads; ++q)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < step) adam_step(pv[j], mv[j], vv[j], g[j], lr_t, P.beta1, P.beta2, P.eps);
-      } else {
+            for (int j = 0; j < 4; ++j)
+              if (j < step) adam_step(pv[q][j], mv[q][j], vv[q][j], gsum[q][j], lr_t, P.beta1, P.beta2, P.eps);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < step) pv[j] = fmaf(-P.lr, g[j], pv[j]);
-      }
-    }
-    if (P.apply_mode == APPLY_MERGED) {
-      if (P.opt == OPT_ADAM) {
-        b1p *= P.beta1;
-        b2p *= P.beta2;
-        const float lr_t = P.lr * sqrtf(1.f - b2p) / (1.f - b1p);
+          for (int q = 0; q < kQuads; ++q)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < step) adam_step(pv[j], mv[j], vv[j], gsum[j], lr_t, P.beta1, P.beta2, P.eps);
-      } else {
+            for (int j = 0; j < 4; ++j)
+              if (j < step) pv[q][j] = fmaf(-P.lr, gsum[q][j], pv[q][j]);
+        }
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < step) pv[j] = fmaf(-P.lr, gsum[j], pv[j]);
+        for (int q = 0; q < kQuads; ++q)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) gsum[q][j] = 0.f;
       }
     }
-    if (vec) {
-      *reinterpret_cast<float4*>(P.params + a) = make_float4(pv[0], pv[1], pv[2], pv[3]);
-      if (P.opt == OPT_ADAM) {
-        *reinterpret_cast<float4*>(P.adam_m + a) = make_float4(mv[0], mv[1], mv[2], mv[3]);
-        *reinterpret_cast<float4*>(P.adam_v + a) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-      }
-      if (P.shadow_bf16 != nullptr && (it.flags & 1)) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(pv[0], pv[1]);
-        __nv_bfloat162 hi = __floats2bfloat162_rn(pv[2], pv[3]);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(P.shadow_bf16 + a) = pk;
-      }
-    } else {
-      P.params[a] = pv[0];
-      if (P.opt == OPT_ADAM) { P.adam_m[a] = mv[0]; P.adam_v[a] = vv[0]; }
-      if (P.shadow_bf16 != nullptr && (it.flags & 1)) {
-        __nv_bfloat16 b = __float2bfloat16(pv[0]);
-        P.shadow_bf16[a] = *reinterpret_cast<uint16_t*>(&b);
+#pragma unroll
+    for (int q = 0; q < kQuads; ++q) {
+      if (!ok[q]) continue;
+      const bool shadow = P.shadow_bf16 != nullptr && (it.flags & 1);
+      if (vec) {
+        *reinterpret_cast<float4*>(P.params + a[q]) = make_float4(pv[q][0], pv[q][1], pv[q][2], pv[q][3]);
+        if (adam) {
+          *reinterpret_cast<float4*>(P.adam_m + a[q]) = make_float4(mv[q][0], mv[q][1], mv[q][2], mv[q][3]);
+          *reinterpret_cast<float4*>(P.adam_v + a[q]) = make_float4(vv[q][0], vv[q][1], vv[q][2], vv[q][3]);
+        }
+        if (shadow) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(pv[q][0], pv[q][1]);
+          __nv_bfloat162 hi = __floats2bfloat162_rn(pv[q][2], pv[q][3]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(P.shadow_bf16 + a[q]) = pk;
+        }
+      } else {
+        P.params[a[q]] = pv[q][0];
+        if (adam) { P.adam_m[a[q]] = mv[q][0]; P.adam_v[a[q]] = vv[q][0]; }
+        if (shadow) {
+          __nv_bfloat16 b = __float2bfloat16(pv[q][0]);
+          P.shadow_bf16[a[q]] = *reinterpret_cast<uint16_t*>(&b);
+        }
       }
     }
   }
 }
 
 __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_constant__ PsServeParams P) {
-  __shared__ uint32_t s_mask;
+  // Everything the poll loop needs about this CTA's items lives in shared memory: the only global traffic of an
+  // idle poll is one acquire load of a flag word per (worker, look-ahead slot).
+  __shared__ PsItem s_item[kMaxOwn];
+  __shared__ PsItemState s_state[kMaxOwn];
+  __shared__ uint32_t s_next[kMaxOwn][kMaxWorkers];  // next expected push seq per (owned item, worker)
   __shared__ uint32_t s_seq[kMaxWorkers];
+  __shared__ uint32_t s_cnt[kMaxWorkers];
+  __shared__ uint32_t s_any;
   __shared__ uint32_t s_exit;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
   uint32_t iter = 0;
+  int n_own = 0;
+  for (int item = blockIdx.x; item < P.n_items && n_own < kMaxOwn; item += gridDim.x) ++n_own;
+  for (int i = tid; i < n_own; i += kPsThreads) {
+    const int item = blockIdx.x + i * gridDim.x;
+    s_item[i] = P.items[item];
+    s_state[i] = P.item_state[item];
+  }
+  for (int i = tid; i < n_own * kMaxWorkers; i += kPsThreads) {
+    const int own = i / kMaxWorkers, w = i - own * kMaxWorkers;
+    s_next[own][w] = w < P.n_workers ? P.next_seq[static_cast<size_t>(w) * P.n_items + blockIdx.x + own * gridDim.x] : 0u;
+  }
+  __syncthreads();
+  // poll lanes: lane -> (worker w, look-ahead k): push s_next + k of worker w. Pushes of one worker are consumed
+  // in order, so only the contiguous ready prefix k = 0 .. cnt-1 is taken in one pass.
+  int kdepth = max(1, min(min(P.nslots, 16), 32 / P.n_workers));
+  if ((P.lookahead & 0xffu) != 0u) kdepth = min(kdepth, static_cast<int>(P.lookahead & 0xffu));
+  const bool dbg_fence = (P.lookahead & 0x100u) != 0u;   // debug: per-thread fence after the apply
+  const int pw = lane / kdepth, pk = lane - pw * kdepth;
+  const bool pvalid = pw < P.n_workers;
 
   for (;;) {
-    bool pending_possible = false;  // some worker may still push to one of my items
-    for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+    for (int own = 0; own < n_own; ++own) {
+      const int item = blockIdx.x + own * gridDim.x;
       if (warp == 0) {
         uint32_t ready = 0, seq = 0;
-        if (lane < P.n_workers) {
-          seq = P.next_seq[static_cast<size_t>(lane) * P.n_items + item];
+        if (pvalid) {
+          seq = s_next[own][pw] + pk;
           const uint32_t slot = seq % P.nslots;
           const uint32_t f = ld_acquire_scoped_u32(
-              P.flags + (static_cast<size_t>(lane) * P.nslots + slot) * P.n_items + item, P.gpu_scope);
+              P.flags + (static_cast<size_t>(pw) * P.nslots + slot) * P.n_items + item, P.gpu_scope);
           ready = (f == seq) ? 1u : 0u;
-          s_seq[lane] = seq;
         }
-        const uint32_t mask = __ballot_sync(0xffffffffu, ready);
-        if (lane == 0) s_mask = mask;
+        const uint32_t b = __ballot_sync(0xffffffffu, ready);
+        uint32_t cnt = 0;
+        if (pvalid && pk == 0) {
+          const uint32_t bits = (b >> lane) & ((1u << kdepth) - 1u);
+          cnt = __ffs(~bits) - 1;   // number of consecutive ready pushes starting at k = 0
+          s_seq[pw] = seq;
+          s_cnt[pw] = cnt;
+        }
+        const uint32_t any = __ballot_sync(0xffffffffu, cnt > 0);
+        if (lane == 0) s_any = any;
       }
       __syncthreads();
-      const uint32_t mask = s_mask;
-      if (mask) {
-        const PsItem it = P.items[item];
-        const PsItemState st = P.item_state[item];
-        apply_item(P, it, st, mask, s_seq);
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-          const int npush = __popc(mask);
-          const int nsteps = (P.apply_mode == APPLY_MERGED) ? 1 : npush;
-          PsItemState ns = st;
-          ns.t += nsteps;
-          for (int k = 0; k < nsteps; ++k) { ns.beta1_pow *= P.beta1; ns.beta2_pow *= P.beta2; }
-          P.item_state[item] = ns;
-          uint32_t mm = mask;
-          while (mm) {
-            const int w = __ffs(mm) - 1;
-            mm &= mm - 1;
-            const uint32_t seq = s_seq[w];
+      if (s_any) {
+        const PsItemState st = s_state[own];
+        uint32_t kmax = 0;
+        for (int w = 0; w < P.n_workers; ++w) kmax = max(kmax, s_cnt[w]);
+        apply_item(P, s_item[own], st, s_seq, s_cnt, kmax);
+        if (dbg_fence) __threadfence();
+        __syncthreads();   // every thread's parameter stores precede warp 0's release operations below
+        if (warp == 0) {
+          if (lane == 0) {
+            uint32_t npush = 0;
+            for (int w = 0; w < P.n_workers; ++w) npush += s_cnt[w];
+            uint32_t rounds = 0;
+            for (int w = 0; w < P.n_workers; ++w) rounds = max(rounds, s_cnt[w]);
+            const uint32_t nsteps = (P.apply_mode == APPLY_MERGED) ? rounds : npush;
+            PsItemState ns = st;
+            ns.t += nsteps;
+            for (uint32_t k = 0; k < nsteps; ++k) { ns.beta1_pow *= P.beta1; ns.beta2_pow *= P.beta2; }
+            s_state[own] = ns;
+            P.item_state[item] = ns;   // persisted for checkpoints / a relaunch (never read back in this loop)
+          }
+          if (pvalid && pk < s_cnt[pw]) {
+            const uint32_t seq = s_seq[pw] + pk;
             const uint32_t slot = seq % P.nslots;
-            P.next_seq[static_cast<size_t>(w) * P.n_items + item] = seq + 1;
-            const uint32_t done = atomicAdd(&P.consumed[w * P.nslots + slot], 1u) + 1u;
+            const uint32_t done = atomicAdd(&P.consumed[pw * P.nslots + slot], 1u) + 1u;
             if (done == static_cast<uint32_t>(P.n_items)) {
               // this worker's push `seq` is fully applied: one global step (reference DS:91,103)
-              P.consumed[w * P.nslots + slot] = 0;
+              P.consumed[pw * P.nslots + slot] = 0;
               const uint32_t gs = atomicAdd(P.global_step, 1u) + 1u;
-              uint32_t* ib = P.inbox_table[w];
+              uint32_t* ib = P.inbox_table[pw];
               if (ib != nullptr) {
-                reinterpret_cast<volatile uint32_t*>(ib)[1] = gs;
-                st_release_scoped_u32(ib, seq, P.gpu_scope);  // ack: the mailbox slot may be reused
+                red_max_relaxed_scoped_u32(ib + 1, gs, P.gpu_scope);
+                red_max_release_scoped_u32(ib, seq, P.gpu_scope);  // ack: the mailbox slot may be reused
               }
             }
+          }
+          __syncwarp();
+          if (pvalid && pk == 0 && s_cnt[pw] > 0) {
+            const uint32_t nx = s_seq[pw] + s_cnt[pw];
+            s_next[own][pw] = nx;
+            P.next_seq[static_cast<size_t>(pw) * P.n_items + item] = nx;
           }
         }
       }
@@ -205,14 +283,13 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
         for (int w = 0; w < P.n_workers && all_done; ++w) {
           const uint32_t d = ld_acquire_sys_u32(P.worker_done + w);  // = last push seq + 1, 0 while active
           if (d == 0) { all_done = false; break; }
-          for (int item = blockIdx.x; item < P.n_items; item += gridDim.x)
-            if (P.next_seq[static_cast<size_t>(w) * P.n_items + item] != d) { all_done = false; break; }
+          for (int own = 0; own < n_own; ++own)
+            if (s_next[own][w] != d) { all_done = false; break; }
         }
         if (all_done) ex = 1;
       }
       s_exit = ex;
     }
-    (void)pending_possible;
     __syncthreads();
     if (s_exit) break;
     ++iter;
@@ -221,8 +298,10 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
 }
 
 cudaError_t launch_ps_serve(const PsServeParams& p, int n_ctas, cudaStream_t stream) {
-  if (p.n_workers > kMaxWorkers) return cudaErrorInvalidValue;
+  if (p.n_workers > kMaxWorkers || p.n_workers < 1) return cudaErrorInvalidValue;
   if (n_ctas > p.n_items) n_ctas = p.n_items;
+  const int min_ctas = (p.n_items + kMaxOwn - 1) / kMaxOwn;  // a CTA caches at most kMaxOwn items
+  if (n_ctas < min_ctas) n_ctas = min_ctas;
   if (n_ctas < 1) n_ctas = 1;
   ps_serve_kernel<<<n_ctas, kPsThreads, 0, stream>>>(p);
   return cudaGetLastError();

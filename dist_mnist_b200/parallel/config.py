@@ -7,7 +7,7 @@ from dataclasses import dataclass, asdict
 from .. import _native as N
 
 
-MAX_LANES = 4
+MAX_SLOTS = 32   # executor ring depth limit (one push-sequence word per slot in the worker segment)
 
 
 def _env_flag(name: str, default: bool) -> bool:
@@ -45,10 +45,12 @@ class EngineConfig:
     ps_ctas: int = 0                 # CTAs of the persistent PS kernel (0 = auto: 120 on a dedicated ps GPU,
                                      # 32 when a worker shares the GPU)
     pipeline_slots: int = 4          # worker executor ring depth
-    lanes: int = 1                   # steps of one worker in flight on the GPU at once (compute streams). 1 = each
-                                     # step starts after the previous one's kernels (reference-like); 2 = step i+1's
-                                     # pull/forward overlaps step i's backward/push (needs nslots >= lanes)
-    pdl: bool = _env_flag("DM_PDL", False)  # programmatic dependent launch between the kernels of a step graph
+    lanes: int = 1                   # steps of one worker in flight on the GPU at once. 1 = each step starts after
+                                     # the previous one's kernels (reference-like); n = step i+1's pull/forward
+                                     # overlaps step i's backward/push (asynchronous SGD; needs nslots >= lanes)
+    graph_steps: int = 1             # steps per CUDA-graph launch in the native loops (U parallel step chains in
+                                     # one graph: one input transfer + one launch per U steps); divides lanes
+    pdl: bool = _env_flag("DM_PDL", True)   # programmatic dependent launch between the kernels of a step graph
     colocate: bool = False           # worker i shares GPU i with ps i (N workers on N GPUs)
 
     @property
@@ -81,12 +83,15 @@ class EngineConfig:
                 raise ValueError("push_mode='atomic' needs the cuda backend")
         if self.nslots < 1:
             raise ValueError("nslots must be >= 1")
-        if self.lanes < 1 or self.lanes > MAX_LANES:
-            raise ValueError(f"lanes must be in [1, {MAX_LANES}]")
+        u = self.graph_steps
+        if self.lanes < 1 or u < 1 or self.lanes % u != 0:
+            raise ValueError("lanes must be a positive multiple of graph_steps")
         if self.push_mode == "mailbox" and self.lanes > self.nslots:
             raise ValueError("lanes (steps in flight) cannot exceed nslots (mailbox slots per worker)")
-        if self.pipeline_slots % self.lanes != 0:
-            raise ValueError("pipeline_slots must be a multiple of lanes")
+        if not (self.lanes <= self.pipeline_slots <= MAX_SLOTS) or self.pipeline_slots % u != 0 \
+                or (self.pipeline_slots // u) % (self.lanes // u) != 0:
+            raise ValueError(f"pipeline_slots must be <= {MAX_SLOTS}, a multiple of graph_steps, and hold a whole "
+                             "number of rounds of lanes")
         _ = self.native_dtype, self.native_apply_mode, opt.native_kind
 
     def as_dict(self) -> dict:

@@ -12,6 +12,8 @@ attaches workers as they register, and blocks in `join()`.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import threading
 import time
@@ -137,6 +139,7 @@ class ParameterServer:
         P.exit_counter = s.addr("ctrl", 4 * CTRL_EXIT_COUNTER)
         P.worker_done = s.addr("ctrl", 4 * CTRL_WORKER_DONE)
         # flags / acks need system scope only when some worker sits on another GPU
+        P.lookahead = int(os.environ.get("DM_PS_LOOKAHEAD", "0"))
         P.gpu_scope = int(cfg.backend == "cuda" and self.n_workers == 1 and len(self._attached_devices) == 1
                           and self._attached_devices[0] == self.device)
         if cfg.backend == "cuda":

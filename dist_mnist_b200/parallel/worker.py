@@ -31,7 +31,7 @@ from ..models import mlp
 from ..models.mlp import MLPSpec
 from ..ops import gemm as gemm_ops
 from ..ops import head as head_ops
-from .config import MAX_LANES, EngineConfig, OptimizerConfig
+from .config import MAX_SLOTS, EngineConfig, OptimizerConfig
 from .peer_mem import Carver, Segment
 from .ps import CTRL_GLOBAL_STEP, CTRL_WORKER_DONE
 from .sharding import ModelLayout, VarLayout, build_layout
@@ -105,7 +105,7 @@ class Worker:
             self.ps_segs.append(Segment.open(desc, device=self.device))
         carver = Carver()
         carver.add("inbox", max(1, len(self.inbox_order)) * 8)
-        carver.add("seq", 4 * (1 + MAX_LANES))   # [0] pushes opened so far, [1 + lane] seq of the lane's current step
+        carver.add("seq", 4 * (1 + MAX_SLOTS))   # [0] pushes opened so far, [1 + slot] seq of the slot's current step
         kind = "cuda" if cfg.backend == "cuda" else "shm"
         self.seg = Segment.create(kind, carver.total, device=self.device, table=carver.table(),
                                   tag=f"w{self.task_index}")
@@ -289,8 +289,8 @@ class Worker:
         x_bytes = self.B_pad * self.ld_in * self.es
         y_bytes = self.B_pad * spec.num_classes * 4
         out = C.c_void_p()
-        N.check(self.lib.dm_exec_create(self.device, cfg.pipeline_slots, cfg.lanes, x_bytes, y_bytes, C.byref(out)),
-                "exec create")
+        N.check(self.lib.dm_exec_create(self.device, cfg.pipeline_slots, cfg.lanes, cfg.graph_steps, x_bytes, y_bytes,
+                                        C.byref(out)), "exec create")
         self._exec = out.value
         self.x_bytes, self.y_bytes = x_bytes, y_bytes
         dev = f"cuda:{self.device}"
@@ -298,9 +298,9 @@ class Worker:
         sizes = spec.layer_sizes
         L = len(sizes)
         # activations / pre-activation gradients of the hidden layers (row padded, zero initialised)
-        # (one set per lane: steps of different lanes run concurrently)
+        # (one set per executor slot: steps of different slots may run concurrently)
         self._lane_act = [[None] + [torch.zeros(self.B_pad, gemm_ops.padded_ld(sizes[l][1]), dtype=self.tdtype,
-                                                device=dev) for l in range(L - 1)] for _ in range(cfg.lanes)]
+                                                device=dev) for l in range(L - 1)] for _ in range(cfg.pipeline_slots)]
         self._lane_dact = [[None] + [torch.zeros_like(a[l + 1]) for l in range(L - 1)] for a in self._lane_act]
         self.act, self.dact = self._lane_act[0], self._lane_dact[0]
         seq_counter = self.seg.addr("seq")
@@ -329,10 +329,9 @@ class Worker:
             act_bf16=cfg.dtype == "bf16", compute_grads=False, ldh=self.act[L - 1].shape[1]))
         torch.cuda.synchronize(self.device)
         for slot in range(cfg.pipeline_slots):
-            lane = slot % cfg.lanes
-            act, dact = self._lane_act[lane], self._lane_dact[lane]
-            seq_ptr = self.seg.addr("seq", 4 * (1 + lane))
-            stream = self.lib.dm_exec_lane_stream(self._exec, lane)
+            act, dact = self._lane_act[slot], self._lane_dact[slot]
+            seq_ptr = self.seg.addr("seq", 4 * (1 + slot))
+            stream = self.lib.dm_exec_capture_stream(self._exec, slot)
             xd, yd, rd, xs, ys = (C.c_void_p() for _ in range(5))
             N.check(self.lib.dm_exec_slot_info(self._exec, slot, C.byref(xd), C.byref(yd), C.byref(rd), C.byref(xs),
                                                C.byref(ys)))
@@ -368,17 +367,15 @@ class Worker:
                 item_w_last_base=wl.item_base, item_b_last=bl.item_base, item_b_hidden_base=hb.item_base,
                 seq_ptr=seq_ptr, inbox_ptr=inbox_ptr, n_inbox=len(self.inbox_order), ps_global_step_ptr=gs_ptr,
                 nslots=cfg.nslots, ldh=act[L - 1].shape[1]))
-            # ---- backward: dW (fused push) and dX (+ bias-grad push) of the hidden layers ----
+            # ---- backward of the hidden layers: dX (+ bias-grad push) *before* dW (fused push) of the same layer:
+            #      dX pulls W_l from the PS a second time, and the PS applies a pushed dW_l within microseconds,
+            #      so pushing dW_l first would let this step's own update leak into its dX ----
             for l in range(L - 2, -1, -1):
                 wn, bn = names[l]
                 wl = lay.by_name[wn]
                 fin, fout = sizes[l]
                 in_ptr = xd.value if l == 0 else act[l].data_ptr()
                 ld_in = self.ld_in if l == 0 else act[l].shape[1]
-                plans.append(gemm_ops.dw_plan(
-                    dy_ptr=dact[l + 1].data_ptr(), x_ptr=in_ptr, O=fout, I=fin, B_pad=self.B_pad, dtype=self.dt,
-                    push=self._push_target(wl.ps, seq_ptr), push_offset=wl.offset, item_base=wl.item_base,
-                    lddy=dact[l + 1].shape[1], ldx=ld_in, ldw=wl.ld, name=f"dw{l}"))
                 if l > 0:
                     pb = lay.by_name[names[l - 1][1]]  # bias of the previous hidden layer gets its grad here
                     plans.append(gemm_ops.dx_plan(
@@ -387,6 +384,10 @@ class Worker:
                         ldw=wl.ld, lddy=dact[l + 1].shape[1], ldo=dact[l].shape[1],
                         colsum=self._push_target(pb.ps, seq_ptr), colsum_offset=pb.offset, colsum_item_base=pb.item_base,
                         name=f"dx{l}"))
+                plans.append(gemm_ops.dw_plan(
+                    dy_ptr=dact[l + 1].data_ptr(), x_ptr=in_ptr, O=fout, I=fin, B_pad=self.B_pad, dtype=self.dt,
+                    push=self._push_target(wl.ps, seq_ptr), push_offset=wl.offset, item_base=wl.item_base,
+                    lddy=dact[l + 1].shape[1], ldx=ld_in, ldw=wl.ld, name=f"dw{l}"))
             if cfg.pdl:
                 # programmatic dependent launch inside the step graph: kernel k+1's prologue (and the head's
                 # W_last fetch) overlaps kernel k; every kernel waits on griddepcontrol.wait before it touches
@@ -407,6 +408,20 @@ class Worker:
                 "x_stage": x_stage.view(self.tdtype).view(self.B_pad, self.ld_in), "x_stage_ptr": xs.value,
                 "y_stage": y_stage.view(torch.float32).view(self.B_pad, spec.num_classes), "y_stage_ptr": ys.value,
             })
+
+        # group graphs: the U steps of a group as parallel chains of one graph (native loops launch these)
+        U = cfg.graph_steps
+        if U > 1:
+            for g in range(cfg.pipeline_slots // U):
+                N.check(self.lib.dm_exec_begin_group_capture(self._exec, g), "begin group capture")
+                try:
+                    for u in range(U):
+                        slot = g * U + u
+                        st = self.lib.dm_exec_capture_stream(self._exec, slot)
+                        for p in self._slots[slot]["plans"]:
+                            p.launch(st)
+                finally:
+                    N.check(self.lib.dm_exec_end_group_capture(self._exec, g), "end group capture")
 
     # ------------------------------------------------------------------------------------------
     # stepping

@@ -12,3 +12,8 @@ def test_smoke_entry_point():
 def test_lockstep_trajectories_all_models_and_modes():
     from bench_tools import gpu_e2e
     assert gpu_e2e.check_traj()
+
+
+def test_pipelined_steps_in_flight_and_group_graphs():
+    from bench_tools import gpu_e2e
+    assert gpu_e2e.check_pipelined()
