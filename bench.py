@@ -249,6 +249,10 @@ def main(argv=None) -> int:
     final_step = worker.read_global_step() if (worker is not None and worker.is_chief) else 0
     full_sync(restart=False)   # serve kernels stay down from here on: torch/NCCL ops below are safe
     clocks = sampler.stop() if clocks_stop_needed else None
+    for ps in ps_list:   # DM_PS_STATS=1: serve-kernel statistics of this rank's shard (diagnostics, stderr)
+        st = ps.serve_stats()
+        if st:
+            print(f"[ps_stats] rank={rank} shard={ps.task_index} {json.dumps(st)}", file=sys.stderr, flush=True)
 
     # ---------------- reduce over ranks ----------------
     kps = worker.kernels_per_step if worker is not None else 0

@@ -43,7 +43,7 @@ def main() -> int:
     args = ap.parse_args()
     dev = "cuda"
     spec = mlp.get_model(args.model)
-    lay = sharding.build_layout(spec, 1)
+    lay = sharding.build_layout(spec, 1, dw_tile_n=sharding.dw_tile_n_for(args.dtype))
     sh = lay.shards[0]
     dt = N.DT_F32 if args.dtype == "fp32" else N.DT_BF16
     tdt = torch.float32 if args.dtype == "fp32" else torch.bfloat16
@@ -117,7 +117,7 @@ def main() -> int:
                                       colsum_offset=pb.offset, colsum_item_base=pb.item_base, name=f"dx{l}"))
         plans.append(gemm.dw_plan(dy_ptr=dact[l + 1].data_ptr(), x_ptr=x.data_ptr() if l == 0 else act[l].data_ptr(),
                                   O=fout, I=fin, B_pad=B_pad, dtype=dt, push=push, push_offset=wl.offset,
-                                  item_base=wl.item_base, lddy=dact[l + 1].shape[1],
+                                  item_base=wl.item_base, bn=lay.dw_tile_n, lddy=dact[l + 1].shape[1],
                                   ldx=ld_in if l == 0 else act[l].shape[1], ldw=wl.ld, name=f"dw{l}"))
 
     if args.pdl:

@@ -173,6 +173,10 @@ struct PsServeParams {
   uint32_t* exit_counter;      // CTAs increment on exit (debug / clean shutdown)
   uint32_t gpu_scope;          // 1: every worker runs on the PS's own GPU (flags / acks at gpu scope)
   uint32_t lookahead;          // max pushes of one worker consumed per item pass (0 = auto: up to nslots)
+  // Optional per-CTA serve statistics [gridDim.x][8] (accumulated over launches, written when a CTA exits):
+  // passes with work, pushes applied, cycles in apply, cycles in bookkeeping, idle poll rounds, cycles idle,
+  // largest number of pushes taken in one pass, poll cycles of working passes. Null = off.
+  unsigned long long* stats;
 };
 
 }  // namespace dm

@@ -18,31 +18,52 @@ namespace dm {
 
 constexpr int kPsThreads = 512;
 constexpr int kMaxOwn = 32;   // items one CTA may own (their descriptors / state / cursors live in shared memory)
-constexpr int kQuads = 2;     // element quads per thread per pass: all their loads are in flight together
+constexpr int kQuads = 2;     // element quads per thread per pass
+constexpr int kChunk = 8;     // pending pushes whose gradient loads are in flight together
+constexpr int kMaxPending = 32;
 
+// MUFU approximations (<= 2 ulp): the Adam update is issue-bound on the one SM that owns an item (IEEE sqrt and
+// divide expand to ~15 instructions each: 3.9 us per push and item measured, 4x the SGD path).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void adam_step(float& p, float& m, float& v, float g, float lr_t, float beta1,
                                           float beta2, float eps) {
   // TF1 AdamOptimizer: m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ; p <- p - lr_t m / (sqrt(v) + eps)
   m = fmaf(beta1, m, (1.f - beta1) * g);
   v = fmaf(beta2, v, (1.f - beta2) * g * g);
-  p -= lr_t * m / (sqrtf(v) + eps);
+  p = fmaf(-lr_t * m, rcp_approx(sqrt_approx(v) + eps), p);
+}
+__device__ __forceinline__ float adam_lr_t(float lr, float b1p, float b2p) {
+  return lr * sqrt_approx(1.f - b2p) * rcp_approx(1.f - b1p);   // lr * sqrt(1 - b2^t) / (1 - b1^t)
 }
 
-// Apply every ready push to one item: worker w contributes its pushes s_seq[w] .. s_seq[w] + s_cnt[w] - 1 (their
-// mailbox slots are all flagged), applied one optimizer step per push in that order (or summed into a single
-// step in APPLY_MERGED mode) while the parameters and Adam slots stay in registers. Called by the whole CTA.
-__device__ void apply_item(const PsServeParams& P, const PsItem it, const PsItemState st, const uint32_t* s_seq,
-                           const uint32_t* s_cnt, const uint32_t kmax) {
+// Apply every pending push to one item. s_pend[0..n_pend) lists the mailbox slots (element offset of the slot
+// inside P.mailbox) in application order — round k = the k-th pending push of every worker, oldest round first —
+// and s_round[i] is the round of entry i. One optimizer step per push, or per round in APPLY_MERGED mode
+// (concurrent pushes of different workers are summed; consecutive pushes of one worker stay separate steps).
+// Parameters and Adam slots stay in registers for the whole pass; the gradient loads of kChunk pushes are issued
+// together (a mailbox line costs an L2/HBM round trip of ~1-2 us: issuing them one push at a time made the
+// pass, and with it the push->ack latency that throttles the workers, proportional to 5 us x pending pushes).
+__device__ void apply_item(const PsServeParams& P, const PsItem it, const PsItemState st, const uint64_t* s_pend,
+                           const uint32_t* s_round, const int n_pend) {
   const int tid = threadIdx.x;
-  const uint64_t wstride = static_cast<uint64_t>(P.nslots) * P.arena_elems;
   const int total = it.rows * it.cols;
   const bool vec = ((it.cols & 3) == 0) && ((it.ld & 3) == 0) && ((it.offset & 3) == 0);
   const int step = vec ? 4 : 1;
   const bool adam = P.opt == OPT_ADAM;
+  const bool merged = P.apply_mode == APPLY_MERGED;
   for (int e0 = tid * step; e0 < total; e0 += kPsThreads * step * kQuads) {
     uint64_t a[kQuads];
     bool ok[kQuads];
-    float pv[kQuads][4], mv[kQuads][4], vv[kQuads][4], gsum[kQuads][4];
+    float pv[kQuads][4], mv[kQuads][4], vv[kQuads][4];
 #pragma unroll
     for (int q = 0; q < kQuads; ++q) {
       const int e = e0 + q * kPsThreads * step;
@@ -51,7 +72,7 @@ __device__ void apply_item(const PsServeParams& P, const PsItem it, const PsItem
       const int c = ok[q] ? e - r * it.cols : 0;
       a[q] = it.offset + static_cast<uint64_t>(r) * it.ld + c;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { pv[q][j] = 0.f; mv[q][j] = 0.f; vv[q][j] = 0.f; gsum[q][j] = 0.f; }
+      for (int j = 0; j < 4; ++j) { pv[q][j] = 0.f; mv[q][j] = 0.f; vv[q][j] = 0.f; }
     }
 #pragma unroll
     for (int q = 0; q < kQuads; ++q) {
@@ -71,71 +92,60 @@ __device__ void apply_item(const PsServeParams& P, const PsItem it, const PsItem
       }
     }
     float b1p = st.beta1_pow, b2p = st.beta2_pow;
-    // round k takes the k-th pending push of every worker (oldest first, workers interleaved). APPLY_MERGED
-    // sums the pushes of one round (concurrent pushes of different workers) into a single optimizer step;
-    // consecutive pushes of the same worker always stay separate steps.
-    for (uint32_t k = 0; k < kmax; ++k) {
-      for (int w = 0; w < P.n_workers; ++w) {
-        if (k >= s_cnt[w]) continue;
-        const uint32_t slot = (s_seq[w] + k) % P.nslots;
-        const float* gbase = P.mailbox + static_cast<uint64_t>(w) * wstride + static_cast<uint64_t>(slot) * P.arena_elems;
-        float g[kQuads][4];
+    float gsum[kQuads][4];
+#pragma unroll
+    for (int q = 0; q < kQuads; ++q)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gsum[q][j] = 0.f;
+
+    for (int i0 = 0; i0 < n_pend; i0 += kChunk) {
+      float g[kChunk][kQuads][4];
+#pragma unroll
+      for (int ci = 0; ci < kChunk; ++ci) {
+        const bool live = i0 + ci < n_pend;
+        const float* gbase = P.mailbox + s_pend[live ? i0 + ci : i0];
 #pragma unroll
         for (int q = 0; q < kQuads; ++q) {
-          g[q][0] = g[q][1] = g[q][2] = g[q][3] = 0.f;
-          if (!ok[q]) continue;
+          g[ci][q][0] = g[ci][q][1] = g[ci][q][2] = g[ci][q][3] = 0.f;
+          if (!ok[q] || !live) continue;
           if (vec) {
             const float4 t = __ldcg(reinterpret_cast<const float4*>(gbase + a[q]));  // L2: written over NVLink
-            g[q][0] = t.x; g[q][1] = t.y; g[q][2] = t.z; g[q][3] = t.w;
+            g[ci][q][0] = t.x; g[ci][q][1] = t.y; g[ci][q][2] = t.z; g[ci][q][3] = t.w;
           } else {
-            g[q][0] = __ldcg(gbase + a[q]);
+            g[ci][q][0] = __ldcg(gbase + a[q]);
           }
         }
-        if (P.apply_mode == APPLY_MERGED) {
-#pragma unroll
-          for (int q = 0; q < kQuads; ++q)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) gsum[q][j] += g[q][j];
-          continue;
-        }
-        if (adam) {
-          b1p *= P.beta1;
-          b2p *= P.beta2;
-          const float lr_t = P.lr * sqrtf(1.f - b2p) / (1.f - b1p);
-#pragma unroll
-          for (int q = 0; q < kQuads; ++q)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j < step) adam_step(pv[q][j], mv[q][j], vv[q][j], g[q][j], lr_t, P.beta1, P.beta2, P.eps);
-        } else {
-#pragma unroll
-          for (int q = 0; q < kQuads; ++q)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j < step) pv[q][j] = fmaf(-P.lr, g[q][j], pv[q][j]);
-        }
       }
-      if (P.apply_mode == APPLY_MERGED) {
+#pragma unroll
+      for (int ci = 0; ci < kChunk; ++ci) {
+        const int i = i0 + ci;
+        if (i >= n_pend) break;
+        bool do_step = true;
+        if (merged) {
+#pragma unroll
+          for (int q = 0; q < kQuads; ++q)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gsum[q][j] += g[ci][q][j];
+          do_step = (i + 1 == n_pend) || (s_round[i + 1] != s_round[i]);   // last push of its round
+        }
+        if (!do_step) continue;
+        float lr_t = P.lr;
         if (adam) {
           b1p *= P.beta1;
           b2p *= P.beta2;
-          const float lr_t = P.lr * sqrtf(1.f - b2p) / (1.f - b1p);
-#pragma unroll
-          for (int q = 0; q < kQuads; ++q)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j < step) adam_step(pv[q][j], mv[q][j], vv[q][j], gsum[q][j], lr_t, P.beta1, P.beta2, P.eps);
-        } else {
-#pragma unroll
-          for (int q = 0; q < kQuads; ++q)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j < step) pv[q][j] = fmaf(-P.lr, gsum[q][j], pv[q][j]);
+          lr_t = adam_lr_t(P.lr, b1p, b2p);
         }
 #pragma unroll
-        for (int q = 0; q < kQuads; ++q)
+        for (int q = 0; q < kQuads; ++q) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) gsum[q][j] = 0.f;
+          for (int j = 0; j < 4; ++j) {
+            if (j >= step) continue;
+            const float gv = merged ? gsum[q][j] : g[ci][q][j];
+            if (adam) adam_step(pv[q][j], mv[q][j], vv[q][j], gv, lr_t, P.beta1, P.beta2, P.eps);
+            else pv[q][j] = fmaf(-P.lr, gv, pv[q][j]);
+            if (merged) gsum[q][j] = 0.f;
+          }
+        }
       }
     }
 #pragma unroll
@@ -176,6 +186,9 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
   __shared__ uint32_t s_next[kMaxOwn][kMaxWorkers];  // next expected push seq per (owned item, worker)
   __shared__ uint32_t s_seq[kMaxWorkers];
   __shared__ uint32_t s_cnt[kMaxWorkers];
+  __shared__ uint64_t s_pend[kMaxPending];
+  __shared__ uint32_t s_round[kMaxPending];
+  __shared__ uint32_t s_npend;
   __shared__ uint32_t s_any;
   __shared__ uint32_t s_exit;
   const int tid = threadIdx.x;
@@ -202,9 +215,15 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
   const int pw = lane / kdepth, pk = lane - pw * kdepth;
   const bool pvalid = pw < P.n_workers;
 
+  // serve statistics (thread 0's view; the CTA barriers make it representative)
+  unsigned long long st_pass = 0, st_push = 0, st_apply = 0, st_book = 0, st_idle_n = 0, st_idle = 0, st_max = 0,
+                     st_poll = 0;
+  const bool stats_on = P.stats != nullptr;
+
   for (;;) {
     for (int own = 0; own < n_own; ++own) {
       const int item = blockIdx.x + own * gridDim.x;
+      const long long c0 = stats_on ? clock64() : 0;
       if (warp == 0) {
         uint32_t ready = 0, seq = 0;
         if (pvalid) {
@@ -223,16 +242,37 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
           s_cnt[pw] = cnt;
         }
         const uint32_t any = __ballot_sync(0xffffffffu, cnt > 0);
-        if (lane == 0) s_any = any;
+        __syncwarp();   // s_seq / s_cnt written by the k == 0 lanes are read by lane 0 below
+        if (lane == 0) {
+          s_any = any;
+          // flat application order: round k = k-th pending push of every worker, oldest round first
+          uint32_t n = 0;
+          if (any) {
+            const uint64_t wstride = static_cast<uint64_t>(P.nslots) * P.arena_elems;
+            for (int k = 0; k < kdepth; ++k)
+              for (int w = 0; w < P.n_workers; ++w)
+                if (static_cast<uint32_t>(k) < s_cnt[w]) {
+                  s_pend[n] = static_cast<uint64_t>(w) * wstride + static_cast<uint64_t>((s_seq[w] + k) % P.nslots) * P.arena_elems;
+                  s_round[n] = k;
+                  ++n;
+                }
+          }
+          s_npend = n;
+        }
       }
       __syncthreads();
+      const long long c1 = stats_on ? clock64() : 0;
+      if (!s_any && stats_on) { ++st_idle_n; st_idle += c1 - c0; }
       if (s_any) {
         const PsItemState st = s_state[own];
-        uint32_t kmax = 0;
-        for (int w = 0; w < P.n_workers; ++w) kmax = max(kmax, s_cnt[w]);
-        apply_item(P, s_item[own], st, s_seq, s_cnt, kmax);
+        apply_item(P, s_item[own], st, s_pend, s_round, static_cast<int>(s_npend));
         if (dbg_fence) __threadfence();
         __syncthreads();   // every thread's parameter stores precede warp 0's release operations below
+        const long long c2 = stats_on ? clock64() : 0;
+        if (stats_on) {
+          ++st_pass; st_push += s_npend; st_apply += c2 - c1; st_poll += c1 - c0;
+          st_max = max(st_max, static_cast<unsigned long long>(s_npend));
+        }
         if (warp == 0) {
           if (lane == 0) {
             uint32_t npush = 0;
@@ -268,6 +308,7 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
             P.next_seq[static_cast<size_t>(pw) * P.n_items + item] = nx;
           }
         }
+        if (stats_on) { __syncwarp(); st_book += clock64() - c2; }
       }
       __syncthreads();
     }
@@ -294,7 +335,14 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
     if (s_exit) break;
     ++iter;
   }
-  if (tid == 0) atomicAdd(P.exit_counter, 1u);
+  if (tid == 0) {
+    if (stats_on) {
+      unsigned long long* o = P.stats + static_cast<size_t>(blockIdx.x) * 8;
+      o[0] += st_pass; o[1] += st_push; o[2] += st_apply; o[3] += st_book; o[4] += st_idle_n; o[5] += st_idle;
+      o[6] = max(o[6], st_max); o[7] += st_poll;
+    }
+    atomicAdd(P.exit_counter, 1u);
+  }
 }
 
 cudaError_t launch_ps_serve(const PsServeParams& p, int n_ctas, cudaStream_t stream) {

@@ -26,7 +26,7 @@ from ..cluster import ClusterSpec, Rendezvous
 from ..models.mlp import MLPSpec
 from .config import EngineConfig, OptimizerConfig
 from .peer_mem import Carver, Segment
-from .sharding import ModelLayout, ShardLayout, build_layout
+from .sharding import ModelLayout, ShardLayout, build_layout, dw_tile_n_for
 
 CTRL_GLOBAL_STEP = 0
 CTRL_HOST_STOP = 1
@@ -52,6 +52,7 @@ def shard_carver(shard: ShardLayout, n_workers: int, nslots: int) -> Carver:
     c.add("item_state", ni * C.sizeof(N.PsItemState))
     c.add("ctrl", CTRL_WORDS * 4)
     c.add("inbox_table", N.MAX_WORKERS * 8)
+    c.add("stats", 160 * 8 * 8)      # per-CTA serve statistics (DM_PS_STATS=1)
     return c
 
 
@@ -65,7 +66,7 @@ class ParameterServer:
         self.cluster, self.task_index, self.spec, self.opt, self.cfg = cluster, task_index, spec, opt, cfg
         self.device = device if cfg.backend == "cuda" else -1
         self.verbose = verbose
-        self.layout = layout or build_layout(spec, cluster.num_ps, cfg.sharding)
+        self.layout = layout or build_layout(spec, cluster.num_ps, cfg.sharding, dw_tile_n_for(cfg.dtype))
         self.shard = self.layout.shards[task_index]
         self.rdv = rdv or Rendezvous(cluster, "ps", task_index)
         self.n_workers = cluster.num_workers
@@ -140,6 +141,7 @@ class ParameterServer:
         P.worker_done = s.addr("ctrl", 4 * CTRL_WORKER_DONE)
         # flags / acks need system scope only when some worker sits on another GPU
         P.lookahead = int(os.environ.get("DM_PS_LOOKAHEAD", "0"))
+        P.stats = s.addr("stats") if (cfg.backend == "cuda" and os.environ.get("DM_PS_STATS") == "1") else None
         P.gpu_scope = int(cfg.backend == "cuda" and self.n_workers == 1 and len(self._attached_devices) == 1
                           and self._attached_devices[0] == self.device)
         if cfg.backend == "cuda":
@@ -251,6 +253,29 @@ class ParameterServer:
                 self.lib.dm_cpu_ps_join(self._cpu_handle)
                 self._cpu_handle = None
         self._serving = False
+
+    def serve_stats(self) -> Optional[dict]:
+        """Aggregated serve-kernel statistics (DM_PS_STATS=1; valid after stop()): per-pass averages over CTAs."""
+        if self.cfg.backend != "cuda" or os.environ.get("DM_PS_STATS") != "1":
+            return None
+        n = 160 * 8
+        host = (C.c_uint64 * n)()
+        N.check(self.lib.dm_memcpy_async(C.addressof(host), self.seg.addr("stats"), 8 * n, None))
+        N.check(self.lib.dm_stream_sync(None))
+        rows = [list(host[i * 8:(i + 1) * 8]) for i in range(160) if host[i * 8] or host[i * 8 + 4]]
+        if not rows:
+            return None
+        tot = [sum(r[j] for r in rows) for j in range(8)]
+        mhz = 1965.0
+        return {
+            "ctas": len(rows), "passes": tot[0], "pushes": tot[1],
+            "pushes_per_pass": round(tot[1] / max(tot[0], 1), 2), "max_pushes_in_pass": max(r[6] for r in rows),
+            "apply_us_per_pass": round(tot[2] / max(tot[0], 1) / mhz, 2),
+            "bookkeeping_us_per_pass": round(tot[3] / max(tot[0], 1) / mhz, 2),
+            "poll_us_per_working_pass": round(tot[7] / max(tot[0], 1) / mhz, 2),
+            "idle_polls": tot[4], "idle_poll_us": round(tot[5] / max(tot[4], 1) / mhz, 2),
+            "busy_fraction": round((tot[2] + tot[3] + tot[7]) / max(tot[2] + tot[3] + tot[7] + tot[5], 1), 3),
+        }
 
     def _serve_ctas(self) -> int:
         """One item per CTA where possible: a dedicated ps GPU gives the serve kernel (almost) every SM, a GPU

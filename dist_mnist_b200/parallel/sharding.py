@@ -105,18 +105,26 @@ class ModelLayout:
     placement: Dict[str, int]
     shards: List[ShardLayout]
     by_name: Dict[str, VarLayout]
+    dw_tile_n: int = DW_TILE_N     # columns of a dW tile == bn of the dW GEMMs == width of a hidden-weight item
 
     def shard_of(self, name: str) -> ShardLayout:
         return self.shards[self.by_name[name].ps]
 
 
-def _items_for(role: str, offset: int, rows: int, cols: int, ld: int) -> List[Item]:
+def dw_tile_n_for(dtype: str) -> int:
+    """dW tile width per compute dtype. fp32 (tf32 MMA, 32-element = 128-byte slabs) uses 32-column tiles: twice
+    the tiles of the 64-column layout, i.e. twice the worker CTAs pushing and twice the ps CTAs applying a push
+    (the per-item apply is what bounds a shard's push rate). bf16 slabs are 64 elements wide."""
+    return 32 if dtype == "fp32" else 64
+
+
+def _items_for(role: str, offset: int, rows: int, cols: int, ld: int, dw_tile_n: int = DW_TILE_N) -> List[Item]:
     items: List[Item] = []
     if role == "hidden_w":
         # tile order == gridDim of the dW GEMM: mtile-major, then ntile (tile = mtile * ntiles + ntile)
         for r0 in range(0, rows, TILE_M):
-            for c0 in range(0, cols, DW_TILE_N):
-                items.append(Item(offset + r0 * ld + c0, min(TILE_M, rows - r0), min(DW_TILE_N, cols - c0), ld, True))
+            for c0 in range(0, cols, dw_tile_n):
+                items.append(Item(offset + r0 * ld + c0, min(TILE_M, rows - r0), min(dw_tile_n, cols - c0), ld, True))
     elif role == "hidden_b":
         for c0 in range(0, cols, TILE_M):
             items.append(Item(offset + c0, 1, min(TILE_M, cols - c0), cols, False))
@@ -131,7 +139,7 @@ def _items_for(role: str, offset: int, rows: int, cols: int, ld: int) -> List[It
     return items
 
 
-def build_layout(spec: MLPSpec, num_ps: int, strategy: str = "round_robin") -> ModelLayout:
+def build_layout(spec: MLPSpec, num_ps: int, strategy: str = "round_robin", dw_tile_n: int = DW_TILE_N) -> ModelLayout:
     placement = place_variables(spec, num_ps, strategy)
     shards = [ShardLayout(ps=k) for k in range(num_ps)]
     shards[placement[GLOBAL_STEP]].owns_global_step = True
@@ -152,7 +160,7 @@ def build_layout(spec: MLPSpec, num_ps: int, strategy: str = "round_robin") -> M
             ld = cols
             span = cols
         offset = _round_up(sh.arena_elems, ALIGN_ELEMS)
-        items = _items_for(role, offset, rows, cols, ld)
+        items = _items_for(role, offset, rows, cols, ld, dw_tile_n)
         vl = VarLayout(spec=v, ps=k, offset=offset, ld=ld, item_base=len(sh.items), n_items=len(items), role=role)
         sh.items.extend(items)
         sh.variables.append(vl)
@@ -160,7 +168,7 @@ def build_layout(spec: MLPSpec, num_ps: int, strategy: str = "round_robin") -> M
         by_name[v.name] = vl
     for sh in shards:
         sh.arena_elems = max(_round_up(sh.arena_elems, ALIGN_ELEMS), ALIGN_ELEMS)
-    return ModelLayout(spec=spec, placement=placement, shards=shards, by_name=by_name)
+    return ModelLayout(spec=spec, placement=placement, shards=shards, by_name=by_name, dw_tile_n=dw_tile_n)
 
 
 def shard_bytes_summary(layout: ModelLayout) -> List[Tuple[int, int, int]]:

@@ -34,7 +34,7 @@ from ..ops import head as head_ops
 from .config import MAX_SLOTS, EngineConfig, OptimizerConfig
 from .peer_mem import Carver, Segment
 from .ps import CTRL_GLOBAL_STEP, CTRL_WORKER_DONE
-from .sharding import ModelLayout, VarLayout, build_layout
+from .sharding import ModelLayout, VarLayout, build_layout, dw_tile_n_for
 
 
 @dataclass
@@ -63,7 +63,7 @@ class Worker:
         self.B_pad = _round_up(batch_size, 16)
         self.device = device if cfg.backend == "cuda" else -1
         self.verbose = verbose
-        self.layout = layout or build_layout(spec, cluster.num_ps, cfg.sharding)
+        self.layout = layout or build_layout(spec, cluster.num_ps, cfg.sharding, dw_tile_n_for(cfg.dtype))
         self.rdv = rdv or Rendezvous(cluster, "worker", task_index)
         self.lib = N.lib()
         self.is_chief = task_index == 0  # DS:108
@@ -387,7 +387,7 @@ class Worker:
                 plans.append(gemm_ops.dw_plan(
                     dy_ptr=dact[l + 1].data_ptr(), x_ptr=in_ptr, O=fout, I=fin, B_pad=self.B_pad, dtype=self.dt,
                     push=self._push_target(wl.ps, seq_ptr), push_offset=wl.offset, item_base=wl.item_base,
-                    lddy=dact[l + 1].shape[1], ldx=ld_in, ldw=wl.ld, name=f"dw{l}"))
+                    bn=lay.dw_tile_n, lddy=dact[l + 1].shape[1], ldx=ld_in, ldw=wl.ld, name=f"dw{l}"))
             if cfg.pdl:
                 # programmatic dependent launch inside the step graph: kernel k+1's prologue (and the head's
                 # W_last fetch) overlaps kernel k; every kernel waits on griddepcontrol.wait before it touches
