@@ -1,0 +1,55 @@
+"""Per-kernel SASS mnemonic evidence of the in-tree library (no GPU needed): `python -m bench_tools.sass_summary`
+rewrites profiles/sass/mnemonic_summary.txt from `cuobjdump -sass dist_mnist_b200/libdmnist_sm100a.so`."""
+import collections
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+KEEP = re.compile(r"^(UTC|LDTM|STTM|UTMA|UBLKCP|SYNCS|RED|ATOM|MEMBAR|CCTL|UCGABAR|ACQBULK|PREEXIT|MUFU\.(RCP|SQRT|RSQ|EX2|LG2)|"
+                  r"ERRBAR|FENCE|LDG\.E\.STRONG|STG\.E\.STRONG|LD\.E\.STRONG|ST\.E\.STRONG|STS\..*CLUSTER|ST\.E.*CLUSTER|MAPA|"
+                  r"UMOV.*SR_CgaCtaId|S2UR)")
+HEADER = """SASS mnemonic evidence per kernel of libdmnist_sm100a.so (cuobjdump -sass, sm_100a); regenerate with
+`python -m bench_tools.sass_summary`.
+UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, UTMALDG = cp.async.bulk.tensor (TMA), UBLKCP = cp.async.bulk,
+SYNCS = mbarrier, UCGABAR = barrier.cluster, ACQBULK / PREEXIT = griddepcontrol.wait / launch_dependents (PDL),
+RED/REDG = red.global (atomic push, monotone acks), *.STRONG.SYS = system-scope flag ld/st, MUFU.RCP/SQRT = Adam fast path
+"""
+
+
+def main() -> int:
+    lib = ROOT / "dist_mnist_b200" / "libdmnist_sm100a.so"
+    txt = subprocess.run(["cuobjdump", "-sass", str(lib)], capture_output=True, text=True, check=True).stdout
+    out = [HEADER]
+    name, counts, n = None, None, 0
+
+    def flush():
+        if name:
+            out.append(name)
+            out.append(f"    instructions: {n}")
+            out.append("    " + ", ".join(f"{k} x{v}" for k, v in sorted(counts.items())))
+            out.append("")
+
+    for line in txt.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            flush()
+            name, counts, n = m.group(1), collections.Counter(), 0
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        if m and name:
+            n += 1
+            op = m.group(1)
+            if KEEP.match(op):
+                counts[op] += 1
+    flush()
+    dst = ROOT / "profiles" / "sass" / "mnemonic_summary.txt"
+    dst.parent.mkdir(parents=True, exist_ok=True)
+    dst.write_text("\n".join(out) + "\n")
+    print(f"wrote {dst} ({len(out)} lines)")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
