@@ -11,12 +11,18 @@ asynchronous per-push apply on the ps) with synthetic 28x28 data and random-init
 
 Two numbers are reported (see the JSON keys):
   value : K steps per worker, inputs streamed from a device-resident 55 000-image dataset (172 MB > L2),
-          timed with CUDA events on the worker's compute stream; the timed region ends with a stream-ordered
-          wait for the PS acknowledgement of the last push, so optimizer applies are inside it.
+          timed with CUDA events on the worker's first run stream; the timed region opens with a fork to the other
+          run streams and ends with a stream-ordered join + wait for the PS acknowledgement of the last push, so
+          every step's kernels and optimizer applies are inside it.
   e2e   : the same K steps through the public API (`Worker.run_steps`): native next_batch gather into pinned
           memory, H2D copy of every batch, step graph, 16-byte result D2H per step; wall clock between
           device synchronisations.
 Both take the max over ranks; throughput = (workers x K) / max elapsed.
+
+Steps in flight: a worker keeps `--lanes` (default 8) consecutive steps in flight on its GPU — asynchronous SGD,
+every step still pulls, computes, pushes and is applied on the ps individually (`gpu_launches` counts every kernel
+of every step); the native loops issue `--graph_steps` (default 4) steps per CUDA-graph launch. `--lanes 1` gives
+the strictly sequential per-worker loop of the reference. The JSON `config` records all three knobs.
 """
 from __future__ import annotations
 
