@@ -210,8 +210,7 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
   // poll lanes: lane -> (worker w, look-ahead k): push s_next + k of worker w. Pushes of one worker are consumed
   // in order, so only the contiguous ready prefix k = 0 .. cnt-1 is taken in one pass.
   int kdepth = max(1, min(min(P.nslots, 16), 32 / P.n_workers));
-  if ((P.lookahead & 0xffu) != 0u) kdepth = min(kdepth, static_cast<int>(P.lookahead & 0xffu));
-  const bool dbg_fence = (P.lookahead & 0x100u) != 0u;   // debug: per-thread fence after the apply
+  if (P.lookahead != 0u) kdepth = min(kdepth, static_cast<int>(P.lookahead));
   const int pw = lane / kdepth, pk = lane - pw * kdepth;
   const bool pvalid = pw < P.n_workers;
 
@@ -266,7 +265,6 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
       if (s_any) {
         const PsItemState st = s_state[own];
         apply_item(P, s_item[own], st, s_pend, s_round, static_cast<int>(s_npend));
-        if (dbg_fence) __threadfence();
         __syncthreads();   // every thread's parameter stores precede warp 0's release operations below
         const long long c2 = stats_on ? clock64() : 0;
         if (stats_on) {

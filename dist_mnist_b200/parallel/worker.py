@@ -299,10 +299,10 @@ class Worker:
         L = len(sizes)
         # activations / pre-activation gradients of the hidden layers (row padded, zero initialised)
         # (one set per executor slot: steps of different slots may run concurrently)
-        self._lane_act = [[None] + [torch.zeros(self.B_pad, gemm_ops.padded_ld(sizes[l][1]), dtype=self.tdtype,
+        self._slot_act = [[None] + [torch.zeros(self.B_pad, gemm_ops.padded_ld(sizes[l][1]), dtype=self.tdtype,
                                                 device=dev) for l in range(L - 1)] for _ in range(cfg.pipeline_slots)]
-        self._lane_dact = [[None] + [torch.zeros_like(a[l + 1]) for l in range(L - 1)] for a in self._lane_act]
-        self.act, self.dact = self._lane_act[0], self._lane_dact[0]
+        self._slot_dact = [[None] + [torch.zeros_like(a[l + 1]) for l in range(L - 1)] for a in self._slot_act]
+        self.act, self.dact = self._slot_act[0], self._slot_dact[0]
         seq_counter = self.seg.addr("seq")
         self._slots = []
         stream = self.lib.dm_exec_compute_stream(self._exec)
@@ -329,7 +329,7 @@ class Worker:
             act_bf16=cfg.dtype == "bf16", compute_grads=False, ldh=self.act[L - 1].shape[1]))
         torch.cuda.synchronize(self.device)
         for slot in range(cfg.pipeline_slots):
-            act, dact = self._lane_act[slot], self._lane_dact[slot]
+            act, dact = self._slot_act[slot], self._slot_dact[slot]
             seq_ptr = self.seg.addr("seq", 4 * (1 + slot))
             stream = self.lib.dm_exec_capture_stream(self._exec, slot)
             xd, yd, rd, xs, ys = (C.c_void_p() for _ in range(5))

@@ -43,3 +43,10 @@ def test_missing_hosts_is_an_error():
     args = cli.build_parser().parse_args(["--job_name", "ps", "--task_index", "0"])
     with pytest.raises(ValueError):
         cli.run(args)
+
+
+def test_engine_flags_default_to_the_sequential_reference_worker():
+    a = cli.build_parser().parse_args([])
+    assert (a.nslots, a.lanes, a.graph_steps) == (2, 1, 1)     # one step at a time per worker, like sess.run
+    a = cli.build_parser().parse_args(["--lanes", "4", "--graph_steps=2", "--nslots", "4"])
+    assert (a.nslots, a.lanes, a.graph_steps) == (4, 4, 2)

@@ -39,6 +39,7 @@ def test_items_tile_every_variable_exactly_once():
         for nps in (1, 2, 3):
             for strat in ("round_robin", "byte_balanced"):
                 _covered(sharding.build_layout(spec, nps, strat))
+                _covered(sharding.build_layout(spec, nps, strat, dw_tile_n=32))
 
 
 def test_book_layout_numbers():
@@ -48,3 +49,14 @@ def test_book_layout_numbers():
     assert sh.n_items == 13 + 1 + 1 + 1
     assert lay.by_name["hid_w"].ld == 784 and lay.by_name["sm_w"].ld == 100
     assert mlp.book_model(100).num_params == 79510
+
+
+def test_dw_tile_width_follows_the_compute_dtype():
+    # fp32 (tf32 MMA, 32-element slabs) uses 32-column dW tiles: twice the items / CTAs per hidden weight
+    assert sharding.dw_tile_n_for("fp32") == 32 and sharding.dw_tile_n_for("bf16") == 64
+    lay = sharding.build_layout(mlp.book_model(100), 1, dw_tile_n=sharding.dw_tile_n_for("fp32"))
+    assert lay.dw_tile_n == 32
+    assert lay.shards[0].n_items == 25 + 1 + 1 + 1     # ceil(784 / 32) dW tiles + hid_b + sm_w + sm_b
+    hid = lay.by_name["hid_w"]
+    tiles = lay.shards[0].items[hid.item_base: hid.item_base + hid.n_items]
+    assert [t.cols for t in tiles] == [32] * 24 + [16] and all(t.rows == 100 for t in tiles)
