@@ -487,7 +487,7 @@ int dm_exec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uint
     std::atomic<bool> quit{false};
     std::mutex plan_mu;
     uint64_t next_group = 0;
-    int n_threads = 3;
+    int n_threads = 4;
     if (const char* e = getenv("DM_GATHER_THREADS")) n_threads = std::max(1, atoi(e));
     n_threads = static_cast<int>(std::min<uint64_t>(n_threads, std::min<uint64_t>(kAhead, n_groups)));
     auto gather_fn = [&] {

@@ -184,8 +184,6 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
   __shared__ PsItem s_item[kMaxOwn];
   __shared__ PsItemState s_state[kMaxOwn];
   __shared__ uint32_t s_next[kMaxOwn][kMaxWorkers];  // next expected push seq per (owned item, worker)
-  __shared__ uint32_t s_seq[kMaxWorkers];
-  __shared__ uint32_t s_cnt[kMaxWorkers];
   __shared__ uint64_t s_pend[kMaxPending];
   __shared__ uint32_t s_round[kMaxPending];
   __shared__ uint32_t s_npend;
@@ -207,12 +205,15 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
     s_next[own][w] = w < P.n_workers ? P.next_seq[static_cast<size_t>(w) * P.n_items + blockIdx.x + own * gridDim.x] : 0u;
   }
   __syncthreads();
-  // poll lanes: lane -> (worker w, look-ahead k): push s_next + k of worker w. Pushes of one worker are consumed
-  // in order, so only the contiguous ready prefix k = 0 .. cnt-1 is taken in one pass.
-  int kdepth = max(1, min(min(P.nslots, 16), 32 / P.n_workers));
+  // poll lanes, round-major: lane = k * n_workers + w checks push s_next[w] + k of worker w. Pushes of one worker
+  // are consumed in order, so only its contiguous ready prefix k = 0 .. cnt-1 is taken in a pass; lane order is
+  // then exactly the application order (round k = k-th pending push of every worker, oldest round first).
+  const int nw = P.n_workers;
+  int kdepth = max(1, min(min(P.nslots, 16), 32 / nw));
   if (P.lookahead != 0u) kdepth = min(kdepth, static_cast<int>(P.lookahead));
-  const int pw = lane / kdepth, pk = lane - pw * kdepth;
-  const bool pvalid = pw < P.n_workers;
+  const int pk = lane / nw, pw = lane - pk * nw;
+  const bool pvalid = pk < kdepth;
+  const uint64_t wstride = static_cast<uint64_t>(P.nslots) * P.arena_elems;
 
   // serve statistics (thread 0's view; the CTA barriers make it representative)
   unsigned long long st_pass = 0, st_push = 0, st_apply = 0, st_book = 0, st_idle_n = 0, st_idle = 0, st_max = 0,
@@ -223,40 +224,30 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
     for (int own = 0; own < n_own; ++own) {
       const int item = blockIdx.x + own * gridDim.x;
       const long long c0 = stats_on ? clock64() : 0;
+      uint32_t p_seq = 0, p_cnt = 0, p_taken = 0;   // warp 0: this lane's push seq, its worker's prefix, all taken
+      bool p_take = false;
       if (warp == 0) {
-        uint32_t ready = 0, seq = 0;
+        uint32_t ready = 0, slot = 0;
         if (pvalid) {
-          seq = s_next[own][pw] + pk;
-          const uint32_t slot = seq % P.nslots;
+          p_seq = s_next[own][pw] + pk;
+          slot = p_seq % P.nslots;
           const uint32_t f = ld_acquire_scoped_u32(
               P.flags + (static_cast<size_t>(pw) * P.nslots + slot) * P.n_items + item, P.gpu_scope);
-          ready = (f == seq) ? 1u : 0u;
+          ready = (f == p_seq) ? 1u : 0u;
         }
         const uint32_t b = __ballot_sync(0xffffffffu, ready);
-        uint32_t cnt = 0;
-        if (pvalid && pk == 0) {
-          const uint32_t bits = (b >> lane) & ((1u << kdepth) - 1u);
-          cnt = __ffs(~bits) - 1;   // number of consecutive ready pushes starting at k = 0
-          s_seq[pw] = seq;
-          s_cnt[pw] = cnt;
+        if (pvalid)
+          while (p_cnt < static_cast<uint32_t>(kdepth) && ((b >> (p_cnt * nw + pw)) & 1u)) ++p_cnt;
+        p_take = pvalid && static_cast<uint32_t>(pk) < p_cnt;
+        p_taken = __ballot_sync(0xffffffffu, p_take);
+        if (p_take) {
+          const int pos = __popc(p_taken & ((1u << lane) - 1u));
+          s_pend[pos] = static_cast<uint64_t>(pw) * wstride + static_cast<uint64_t>(slot) * P.arena_elems;
+          s_round[pos] = pk;
         }
-        const uint32_t any = __ballot_sync(0xffffffffu, cnt > 0);
-        __syncwarp();   // s_seq / s_cnt written by the k == 0 lanes are read by lane 0 below
         if (lane == 0) {
-          s_any = any;
-          // flat application order: round k = k-th pending push of every worker, oldest round first
-          uint32_t n = 0;
-          if (any) {
-            const uint64_t wstride = static_cast<uint64_t>(P.nslots) * P.arena_elems;
-            for (int k = 0; k < kdepth; ++k)
-              for (int w = 0; w < P.n_workers; ++w)
-                if (static_cast<uint32_t>(k) < s_cnt[w]) {
-                  s_pend[n] = static_cast<uint64_t>(w) * wstride + static_cast<uint64_t>((s_seq[w] + k) % P.nslots) * P.arena_elems;
-                  s_round[n] = k;
-                  ++n;
-                }
-          }
-          s_npend = n;
+          s_any = p_taken;
+          s_npend = __popc(p_taken);
         }
       }
       __syncthreads();
@@ -273,10 +264,8 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
         }
         if (warp == 0) {
           if (lane == 0) {
-            uint32_t npush = 0;
-            for (int w = 0; w < P.n_workers; ++w) npush += s_cnt[w];
-            uint32_t rounds = 0;
-            for (int w = 0; w < P.n_workers; ++w) rounds = max(rounds, s_cnt[w]);
+            const uint32_t npush = __popc(p_taken);
+            const uint32_t rounds = (31u - __clz(p_taken)) / nw + 1u;   // lanes are round-major
             const uint32_t nsteps = (P.apply_mode == APPLY_MERGED) ? rounds : npush;
             PsItemState ns = st;
             ns.t += nsteps;
@@ -284,24 +273,22 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
             s_state[own] = ns;
             P.item_state[item] = ns;   // persisted for checkpoints / a relaunch (never read back in this loop)
           }
-          if (pvalid && pk < s_cnt[pw]) {
-            const uint32_t seq = s_seq[pw] + pk;
-            const uint32_t slot = seq % P.nslots;
+          if (p_take) {
+            const uint32_t slot = p_seq % P.nslots;
             const uint32_t done = atomicAdd(&P.consumed[pw * P.nslots + slot], 1u) + 1u;
             if (done == static_cast<uint32_t>(P.n_items)) {
-              // this worker's push `seq` is fully applied: one global step (reference DS:91,103)
+              // this worker's push `p_seq` is fully applied: one global step (reference DS:91,103)
               P.consumed[pw * P.nslots + slot] = 0;
               const uint32_t gs = atomicAdd(P.global_step, 1u) + 1u;
               uint32_t* ib = P.inbox_table[pw];
               if (ib != nullptr) {
                 red_max_relaxed_scoped_u32(ib + 1, gs, P.gpu_scope);
-                red_max_release_scoped_u32(ib, seq, P.gpu_scope);  // ack: the mailbox slot may be reused
+                red_max_release_scoped_u32(ib, p_seq, P.gpu_scope);  // ack: the mailbox slot may be reused
               }
             }
           }
-          __syncwarp();
-          if (pvalid && pk == 0 && s_cnt[pw] > 0) {
-            const uint32_t nx = s_seq[pw] + s_cnt[pw];
+          if (pvalid && pk == 0 && p_cnt > 0) {
+            const uint32_t nx = p_seq + p_cnt;
             s_next[own][pw] = nx;
             P.next_seq[static_cast<size_t>(pw) * P.n_items + item] = nx;
           }

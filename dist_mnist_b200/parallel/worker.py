@@ -17,6 +17,7 @@ CPU backend: same protocol over POSIX shm with torch CPU math (BASELINE.json con
 """
 from __future__ import annotations
 
+import collections.abc
 import ctypes as C
 import time
 from dataclasses import dataclass
@@ -43,6 +44,32 @@ class StepOutput:
     global_step: int
     correct: int
     seq: int
+
+
+_STEP_DTYPE = np.dtype([("loss", np.float32), ("global_step", np.uint32), ("correct", np.uint32), ("seq", np.uint32)])
+
+
+class StepOutputs(collections.abc.Sequence):
+    """Results of a native run of steps: a read-only sequence of `StepOutput` backed by the executor's result
+    array (no per-step Python object is built unless the step is looked at). `.loss`, `.global_step`, `.correct`
+    and `.seq` give the whole columns as numpy arrays."""
+
+    def __init__(self, raw: np.ndarray):
+        self._raw = raw
+
+    def __len__(self) -> int:
+        return int(self._raw.shape[0])
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return StepOutputs(self._raw[i])
+        r = self._raw[i]
+        return StepOutput(float(r["loss"]), int(r["global_step"]), int(r["correct"]), int(r["seq"]))
+
+    loss = property(lambda self: self._raw["loss"])
+    global_step = property(lambda self: self._raw["global_step"])
+    correct = property(lambda self: self._raw["correct"])
+    seq = property(lambda self: self._raw["seq"])
 
 
 def _round_up(a: int, b: int) -> int:
@@ -476,7 +503,7 @@ class Worker:
         """Native `next_batch` loader over a host dataset (kept alive by the returned object)."""
         return NativeLoader(self, images, labels, seed, shuffle)
 
-    def run_steps(self, n_steps: int, loader: "NativeLoader", stop_at_global_step: int = 0) -> List[StepOutput]:
+    def run_steps(self, n_steps: int, loader: "NativeLoader", stop_at_global_step: int = 0) -> Sequence[StepOutput]:
         """Native train loop: n_steps x (next_batch -> H2D -> step graph -> result D2H)."""
         if self.cfg.backend != "cuda":
             out = []
@@ -491,7 +518,8 @@ class Worker:
         done = C.c_uint64()
         N.check(self.lib.dm_exec_run(self._exec, loader.handle, n_steps, C.addressof(res), stop_at_global_step,
                                      C.byref(done)), "exec run")
-        return [StepOutput(res[i].loss, res[i].global_step, res[i].correct, res[i].seq) for i in range(done.value)]
+        raw = np.frombuffer(res, dtype=_STEP_DTYPE, count=n_steps)[: done.value]   # keeps `res` alive
+        return StepOutputs(raw)
 
     def drain(self) -> None:
         if self._exec:
