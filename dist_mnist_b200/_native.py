@@ -114,6 +114,7 @@ _MIRRORS = {
     "PsItem": PsItem, "PsItemState": PsItemState, "PsServeParams": PsServeParams,
 }
 
+WORKER_DEAD = 0xFFFFFFFF   # protocol.h kWorkerDead
 TENSOR_MAP_BYTES = 128
 
 

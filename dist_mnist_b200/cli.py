@@ -71,6 +71,11 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--colocate", action="store_true", help="worker i shares GPU i with ps i")
     p.add_argument("--log_every", type=int, default=100)
     p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--worker_timeout", type=float, default=0.0,
+                   help="ps: declare a worker dead after this many seconds without a heartbeat and stop waiting for "
+                        "it (0 = never, like the reference)")
+    p.add_argument("--inject_fault", type=int, default=0,
+                   help="worker: crash (os._exit) after this many local steps — fault-injection hook for tests")
     p.add_argument("--ps_exit_when_done", action="store_true",
                    help="let a ps task return once every worker has finished (reference ps blocks forever)")
     p.add_argument("--rendezvous_timeout", type=float, default=300.0)
@@ -121,7 +126,8 @@ def run(args: argparse.Namespace) -> int:
         ps = ParameterServer(cluster, args.task_index, spec, opt, cfg, device=device, rdv=rdv)
         ps.start()
         try:
-            ps.join(exit_when_done=args.ps_exit_when_done)  # DS:83 — blocks forever unless asked otherwise
+            # DS:83 — blocks forever unless asked otherwise
+            ps.join(exit_when_done=args.ps_exit_when_done, worker_timeout_s=args.worker_timeout)
         except KeyboardInterrupt:
             pass
         finally:
@@ -141,7 +147,7 @@ def run(args: argparse.Namespace) -> int:
     try:
         train_loop(worker, dataset, train_steps=args.train_steps, log_every=args.log_every,
                    checkpoint_dir=args.checkpoint_dir, save_checkpoint_secs=args.save_checkpoint_secs,
-                   seed=args.seed)
+                   seed=args.seed, inject_fault_after=args.inject_fault)
     finally:
         worker.close()
     return 0

@@ -144,6 +144,7 @@ void serve_loop(CpuPs* ps) {
     for (int w = 0; w < P.n_workers && all_done; ++w) {
       const uint32_t d = load_acquire(P.worker_done + w);
       if (d == 0) { all_done = false; break; }
+      if (d == dm::kWorkerDead) continue;   // presumed dead (ps host failure detector)
       for (int item = 0; item < P.n_items; ++item)
         if (P.next_seq[static_cast<size_t>(w) * P.n_items + item] != d) { all_done = false; break; }
     }

@@ -17,6 +17,9 @@
 namespace dm {
 
 constexpr int kMaxWorkers = 32;
+// worker_done[w] sentinel written by the ps host when worker w is presumed dead (no heartbeat): the serve kernel /
+// loop stops waiting for its pushes when it decides whether every worker has left.
+constexpr uint32_t kWorkerDead = 0xFFFFFFFFu;
 
 enum PushMode : int {
   PUSH_LOCAL = 0,    // plain store into a local fp32 gradient buffer (tests, NCCL baseline)

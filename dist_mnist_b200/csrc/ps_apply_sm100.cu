@@ -309,6 +309,7 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
         for (int w = 0; w < P.n_workers && all_done; ++w) {
           const uint32_t d = ld_acquire_sys_u32(P.worker_done + w);  // = last push seq + 1, 0 while active
           if (d == 0) { all_done = false; break; }
+          if (d == kWorkerDead) continue;   // presumed dead: whatever it left half-pushed is dropped
           for (int own = 0; own < n_own; ++own)
             if (s_next[own][w] != d) { all_done = false; break; }
         }

@@ -80,6 +80,7 @@ class ParameterServer:
         self._pin = None
         self._cpu_table = (C.c_void_p * N.MAX_WORKERS)() if cfg.backend == "cpu" else None
         self._lock = threading.Lock()
+        self._dead = set()          # workers declared dead by the failure detector
 
         kind = "cuda" if cfg.backend == "cuda" else "shm"
         if kind == "cuda":
@@ -306,13 +307,67 @@ class ParameterServer:
             self._cpu_handle = self.lib.dm_cpu_ps_start(C.addressof(self._P))
         self._serving = True
 
-    def join(self, exit_when_done: bool = False, poll_s: float = 0.05) -> None:
+    def _worker_done_word(self, w: int) -> int:
+        addr = self.seg.addr("ctrl", 4 * (CTRL_WORKER_DONE + w))
+        if self.cfg.backend == "cuda":
+            host = C.c_uint32(0)
+            N.check(self.lib.dm_memcpy_async(C.addressof(host), addr, 4, self._ctl_stream))
+            N.check(self.lib.dm_stream_sync(self._ctl_stream))
+            return host.value
+        return self.lib.dm_load_acquire_u32(addr)
+
+    def mark_worker_dead(self, w: int) -> None:
+        """Failure handling: stop waiting for worker `w` (its half-finished push, if any, is dropped; everything it
+        pushed completely stays applied). Asynchronous training means the other workers never depended on it."""
+        self._patch_table(w, 0)     # no more acknowledgements into the dead process's memory
+        addr = self.seg.addr("ctrl", 4 * (CTRL_WORKER_DONE + w))
+        if self.cfg.backend == "cuda":
+            C.c_uint32.from_address(self._pin + 1028).value = N.WORKER_DEAD
+            N.check(self.lib.dm_memcpy_async(addr, self._pin + 1028, 4, self._ctl_stream))
+            N.check(self.lib.dm_stream_sync(self._ctl_stream))
+        else:
+            self.lib.dm_store_release_u32(addr, N.WORKER_DEAD)
+        self._dead.add(w)
+
+    def check_worker_liveness(self, timeout_s: float) -> List[int]:
+        """Declare dead every attached worker that has neither finished nor sent a heartbeat for `timeout_s`
+        seconds (workers heartbeat through the rendezvous store once per train-loop chunk). Returns the workers
+        newly declared dead."""
+        newly = []
+        now = time.time()
+        for w in list(self._attached):
+            if w in self._dead:
+                continue
+            hb = self.rdv.try_get(f"session/heartbeat/{w}")
+            if hb is None or now - float(hb) <= timeout_s:
+                continue
+            if self.cfg.push_mode != "atomic" and self._worker_done_word(w) != 0:
+                continue   # it left the session cleanly
+            if self.cfg.push_mode == "atomic" and self.rdv.try_get(f"session/done/{w}") is not None:
+                continue
+            print(f"[ps {self.task_index}] worker {w} presumed dead: no heartbeat for {now - float(hb):.1f} s; "
+                  f"serving the remaining workers", flush=True)
+            if self.cfg.push_mode != "atomic":
+                self.mark_worker_dead(w)
+            else:
+                self._dead.add(w)
+                if self.task_index == 0:
+                    self.rdv.add("session/workers_done", 1)
+            newly.append(w)
+        return newly
+
+    def join(self, exit_when_done: bool = False, poll_s: float = 0.05, worker_timeout_s: float = 0.0) -> None:
         """`server.join()` (DS:83): block forever serving. With `exit_when_done` the call returns once every
-        worker has left the session and all their pushes are applied, or when a `shutdown` mark appears."""
+        worker has left the session (or is presumed dead, `worker_timeout_s > 0`) and all their pushes are applied,
+        or when a `shutdown` mark appears."""
+        last_check = time.time()
         while True:
             self.attach_registered_workers()
             if self.rdv.try_get("shutdown") is not None:
                 break
+            if worker_timeout_s > 0 and time.time() - last_check >= min(1.0, worker_timeout_s / 2):
+                last_check = time.time()
+                self.check_worker_liveness(worker_timeout_s)
             if exit_when_done:
                 if self.cfg.push_mode == "atomic":
                     if self.rdv.add("session/workers_done", 0) >= self.n_workers:

@@ -140,6 +140,7 @@ class Worker:
         desc["inbox_index"] = {str(k): i for k, i in self.inbox_index.items()}
         desc["worker_device"] = self.device
         self.rdv.put(f"worker/{self.task_index}/inbox", desc)
+        self.heartbeat()
         self._connected = True
 
     def wait_ready(self, timeout_s: Optional[float] = None) -> None:
@@ -187,6 +188,10 @@ class Worker:
             if time.time() - t0 > timeout_s:
                 raise TimeoutError(f"pushes up to {seq} not acknowledged: inbox={inbox}")
             time.sleep(0.0005)
+
+    def heartbeat(self) -> None:
+        """Liveness mark for the ps-side failure detector (`ParameterServer.join(worker_timeout_s=...)`)."""
+        self.rdv.put(f"session/heartbeat/{self.task_index}", time.time())
 
     def prepare(self) -> None:
         """Build the step graphs (GPU backend). Only needs the PS pointers, so it may run before the variables
@@ -656,6 +661,7 @@ class Worker:
                 for k in self.inbox_order:
                     self.lib.dm_store_release_u32(self.ps_segs[k].addr("ctrl", 4 * (CTRL_WORKER_DONE + w)),
                                                   self._seq_host + 1)
+        self.rdv.put(f"session/done/{w}", 1)
         self.rdv.add("session/workers_done", 1)
 
     def close(self) -> None:

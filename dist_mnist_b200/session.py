@@ -9,6 +9,7 @@ Reference parity (`/root/reference/distributed_server-basic.py`):
 from __future__ import annotations
 
 import socket
+import os
 import tempfile
 import time
 from dataclasses import dataclass
@@ -89,7 +90,8 @@ class TrainLoopResult:
 
 def train_loop(worker: Worker, dataset: Dataset, train_steps: int = 4000, log_every: int = 100,
                checkpoint_dir: Optional[str] = None, save_checkpoint_secs: float = 600.0, seed: int = 0,
-               chunk: int = 50, print_fn: Callable[[str], None] = print) -> TrainLoopResult:
+               chunk: int = 50, print_fn: Callable[[str], None] = print,
+               inject_fault_after: int = 0) -> TrainLoopResult:
     """The worker's `MonitoredTrainingSession` loop (DS:106-116).
 
     Runs until a step reports `global_step >= train_steps` (StopAtStepHook on the shared counter), printing
@@ -107,8 +109,13 @@ def train_loop(worker: Worker, dataset: Dataset, train_steps: int = 4000, log_ev
     ckpt_path = None
     stop = False
     while not stop:
+        worker.heartbeat()     # liveness mark for the ps-side failure detector (--worker_timeout)
         outs = worker.run_steps(chunk, loader, stop_at_global_step=train_steps)
         steps_run += len(outs)
+        if inject_fault_after and steps_run >= inject_fault_after:
+            # fault injection (tests): die like a crashed process — no finish(), no close(), no atexit handlers
+            print(f"[fault injection] worker {worker.task_index} dies after {steps_run} steps", flush=True)
+            os._exit(42)
         for o in outs:
             last = o
             if log_every and o.global_step % log_every == 0:

@@ -86,3 +86,24 @@ def test_bad_invocations():
                        capture_output=True, text=True, env=env)
     assert r.returncode != 0 and "Must specify a valid task index" in r.stderr
     assert "job name : worker" in r.stdout
+
+
+@pytest.mark.timeout(240)
+def test_worker_crash_is_detected_and_training_continues():
+    """Failure detection: worker 1 crashes mid-run (fault injection); the ps declares it dead after
+    `--worker_timeout` seconds without a heartbeat, worker 0 trains on to the target global step, and the ps
+    (asked to exit when done) does not wait for the dead worker forever."""
+    ps_hosts = f"127.0.0.1:{_free_port()}"
+    worker_hosts = f"127.0.0.1:{_free_port()},127.0.0.1:{_free_port()}"
+    common = ["--train_steps", "600", "--learning_rate", "0.001"]
+    ps = _spawn("ps", 0, ps_hosts, worker_hosts, common + ["--ps_exit_when_done", "--worker_timeout", "3"])
+    w0 = _spawn("worker", 0, ps_hosts, worker_hosts, common)
+    w1 = _spawn("worker", 1, ps_hosts, worker_hosts, common + ["--inject_fault", "50"])
+    out1 = _finish(w1, 120)
+    assert w1.returncode == 42 and "[fault injection] worker 1 dies" in out1, out1
+    out0 = _finish(w0, 150)
+    assert w0.returncode == 0, out0
+    assert "Train step 600, loss:" in out0 or "Train step 500, loss:" in out0, out0
+    outp = _finish(ps, 60)
+    assert ps.returncode == 0, outp
+    assert "worker 1 presumed dead" in outp, outp
