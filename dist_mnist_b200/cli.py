@@ -34,6 +34,7 @@ from .parallel.worker import Worker
 from .session import train_loop
 from .utils import ckpt as ckpt_utils
 from .utils import data as data_utils
+from .utils.metrics import TrainMetricsWriter
 
 
 def build_parser() -> argparse.ArgumentParser:
@@ -71,6 +72,10 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--colocate", action="store_true", help="worker i shares GPU i with ps i")
     p.add_argument("--log_every", type=int, default=100)
     p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--metrics_file", type=str, default=None,
+                   help="worker: append one JSON line per --log_every local steps (loss, batch accuracy, steps/sec)")
+    p.add_argument("--log_steps_per_sec", action="store_true",
+                   help="worker: also print the reference's implicit StepCounterHook line (global_step/sec)")
     p.add_argument("--worker_timeout", type=float, default=0.0,
                    help="ps: declare a worker dead after this many seconds without a heartbeat and stop waiting for "
                         "it (0 = never, like the reference)")
@@ -144,11 +149,17 @@ def run(args: argparse.Namespace) -> int:
         else:
             worker.mark_initialized()
     worker.wait_ready()
+    metrics = None
+    if args.metrics_file or args.log_steps_per_sec:
+        metrics = TrainMetricsWriter(args.metrics_file, args.task_index, args.batch_size,
+                                     every_steps=max(1, args.log_every), echo=args.log_steps_per_sec)
     try:
         train_loop(worker, dataset, train_steps=args.train_steps, log_every=args.log_every,
                    checkpoint_dir=args.checkpoint_dir, save_checkpoint_secs=args.save_checkpoint_secs,
-                   seed=args.seed, inject_fault_after=args.inject_fault)
+                   seed=args.seed, inject_fault_after=args.inject_fault, metrics=metrics)
     finally:
+        if metrics is not None:
+            metrics.close()
         worker.close()
     return 0
 

@@ -18,6 +18,7 @@ from typing import Callable, Dict, List, Optional
 import torch
 
 from .cluster import ClusterSpec, Rendezvous
+from .utils.metrics import TrainMetricsWriter
 from .models.mlp import MLPSpec
 from .parallel.config import EngineConfig, OptimizerConfig
 from .parallel.ps import ParameterServer
@@ -91,7 +92,7 @@ class TrainLoopResult:
 def train_loop(worker: Worker, dataset: Dataset, train_steps: int = 4000, log_every: int = 100,
                checkpoint_dir: Optional[str] = None, save_checkpoint_secs: float = 600.0, seed: int = 0,
                chunk: int = 50, print_fn: Callable[[str], None] = print,
-               inject_fault_after: int = 0) -> TrainLoopResult:
+               inject_fault_after: int = 0, metrics: Optional["TrainMetricsWriter"] = None) -> TrainLoopResult:
     """The worker's `MonitoredTrainingSession` loop (DS:106-116).
 
     Runs until a step reports `global_step >= train_steps` (StopAtStepHook on the shared counter), printing
@@ -116,6 +117,8 @@ def train_loop(worker: Worker, dataset: Dataset, train_steps: int = 4000, log_ev
             # fault injection (tests): die like a crashed process — no finish(), no close(), no atexit handlers
             print(f"[fault injection] worker {worker.task_index} dies after {steps_run} steps", flush=True)
             os._exit(42)
+        if metrics is not None:
+            metrics.update(outs)
         for o in outs:
             last = o
             if log_every and o.global_step % log_every == 0:

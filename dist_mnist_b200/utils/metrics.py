@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import csv
 import io
+import json
 import shutil
 import statistics
 import subprocess
@@ -105,3 +106,58 @@ class StreamTimer:
     def elapsed_ms(self) -> float:
         self.t1.synchronize()
         return self.t0.elapsed_time(self.t1)
+
+
+class TrainMetricsWriter:
+    """The reference's implicit `StepCounterHook` / `SummarySaverHook` (MonitoredTrainingSession defaults, SURVEY
+    §3.4): every `every_steps` local steps one JSON line {time, worker, local_steps, global_step, loss,
+    batch_accuracy, steps_per_sec} is appended to `path` (accuracy comes for free: the head kernel counts the
+    correct predictions of every training batch), and optionally an INFO-style `global_step/sec` line is printed."""
+
+    def __init__(self, path: Optional[str], worker_index: int, batch_size: int, every_steps: int = 100,
+                 echo: bool = False, print_fn=print):
+        self.path, self.worker, self.batch, self.every, self.echo, self.print_fn = (
+            path, worker_index, batch_size, max(1, every_steps), echo, print_fn)
+        self._fh = open(path, "a") if path else None
+        self._t_last = time.time()
+        self._steps = 0
+        self._steps_last = 0
+        self._gs_last: Optional[int] = None
+        self._loss_sum = 0.0
+        self._correct = 0
+        self._n = 0
+
+    def update(self, outs) -> None:
+        """Feed the results of a run of steps (any sequence of StepOutput)."""
+        for o in outs:
+            self._steps += 1
+            self._loss_sum += o.loss
+            self._correct += o.correct
+            self._n += 1
+            if self._steps - self._steps_last >= self.every:
+                self._emit(o.global_step)
+
+    def _emit(self, global_step: int) -> None:
+        now = time.time()
+        dt = max(now - self._t_last, 1e-9)
+        rec = {
+            "time": round(now, 3), "worker": self.worker, "local_steps": self._steps, "global_step": int(global_step),
+            "loss": self._loss_sum / max(self._n, 1),
+            "batch_accuracy": self._correct / max(self._n * self.batch, 1),
+            "steps_per_sec": (self._steps - self._steps_last) / dt,
+        }
+        if self._gs_last is not None:
+            rec["global_steps_per_sec"] = (int(global_step) - self._gs_last) / dt
+        if self._fh:
+            self._fh.write(json.dumps(rec) + "\n")
+            self._fh.flush()
+        if self.echo:
+            self.print_fn("INFO global_step/sec: {:.1f} (this worker {:.1f} steps/sec, batch accuracy {:.3f})".format(
+                rec.get("global_steps_per_sec", rec["steps_per_sec"]), rec["steps_per_sec"], rec["batch_accuracy"]))
+        self._t_last, self._steps_last, self._gs_last = now, self._steps, int(global_step)
+        self._loss_sum, self._correct, self._n = 0.0, 0, 0
+
+    def close(self) -> None:
+        if self._fh:
+            self._fh.close()
+            self._fh = None

@@ -126,3 +126,22 @@ def test_config_validation():
     with pytest.raises(ValueError):
         EngineConfig(dtype="fp8").validate(OptimizerConfig("adam"))
     EngineConfig(backend="cuda", push_mode="atomic").validate(OptimizerConfig("sgd"))
+
+
+def test_train_metrics_writer_jsonl(tmp_path, capsys):
+    """StepCounterHook / SummarySaverHook analogue: one JSON line per `every_steps` local steps."""
+    import json
+    from dist_mnist_b200.utils.metrics import TrainMetricsWriter
+    spec = mlp.book_model(64)
+    ds = data.synthetic_mnist(512, seed=0)
+    path = tmp_path / "metrics.jsonl"
+    with InProcessCluster(spec, OptimizerConfig("adam", 1e-3), EngineConfig(backend="cpu"), batch_size=32) as cl:
+        m = TrainMetricsWriter(str(path), worker_index=0, batch_size=32, every_steps=20, echo=True)
+        train_loop(cl.worker, ds, train_steps=100, log_every=0, chunk=10, metrics=m)
+        m.close()
+    recs = [json.loads(l) for l in path.read_text().splitlines()]
+    assert [r["local_steps"] for r in recs] == [20, 40, 60, 80, 100]
+    assert recs[-1]["global_step"] == 100 and all(r["steps_per_sec"] > 0 for r in recs)
+    assert recs[-1]["loss"] < recs[0]["loss"] and 0.0 <= recs[0]["batch_accuracy"] <= 1.0
+    assert recs[-1]["batch_accuracy"] > recs[0]["batch_accuracy"]
+    assert sum(l.startswith("INFO global_step/sec:") for l in capsys.readouterr().out.splitlines()) == 5
