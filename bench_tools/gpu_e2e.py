@@ -146,6 +146,7 @@ def check_throughput(only=None) -> bool:
 
 
 PIPE_CASES = [("book", "adam", "fp32", "mailbox", 2, 1, False), ("book", "adam", "fp32", "mailbox", 4, 2, True),
+              ("book", "adam", "fp32", "mailbox", 4, 2, True, True),      # classifier head fused into the forward GEMM
               ("book", "sgd", "fp32", "atomic", 4, 4, True), ("wide", "adam", "bf16", "mailbox", 4, 2, True),
               ("zhihu", "sgd", "fp32", "mailbox", 2, 2, False)]
 
@@ -157,13 +158,15 @@ def check_pipelined(only=None) -> bool:
     of the native loop are exercised next to the group launches."""
     ok = True
     ds = data.synthetic_mnist(8192, seed=0)
-    for (model, okind, dtype, push, lanes, gsteps, pdl) in (PIPE_CASES if only is None else [PIPE_CASES[only]]):
-        name = f"pipelined model={model} opt={okind} dtype={dtype} push={push} lanes={lanes} graph_steps={gsteps} pdl={pdl}"
+    for case in (PIPE_CASES if only is None else [PIPE_CASES[only]]):
+        (model, okind, dtype, push, lanes, gsteps, pdl), fuse = case[:7], (len(case) > 7 and case[7])
+        name = (f"pipelined model={model} opt={okind} dtype={dtype} push={push} lanes={lanes} graph_steps={gsteps} "
+                f"pdl={pdl} fuse_head={fuse}")
         try:
             spec = mlp.get_model(model)
             opt = OptimizerConfig(okind, 1e-3 if okind == "adam" else 1e-2)
             cfg = EngineConfig(backend="cuda", dtype=dtype, push_mode=push, lanes=lanes, graph_steps=gsteps,
-                               nslots=max(2, lanes), pipeline_slots=max(4, 2 * lanes), pdl=pdl)
+                               nslots=max(2, lanes), pipeline_slots=max(4, 2 * lanes), pdl=pdl, fuse_head=fuse)
             with InProcessCluster(spec, opt, cfg, batch_size=32) as cl:
                 w = cl.worker
                 loader = w.make_loader(ds.images, ds.labels, seed=0)
@@ -179,7 +182,11 @@ def check_pipelined(only=None) -> bool:
                 seqs = sorted(o.seq for o in outs)
                 first = sum(o.loss for o in outs[:20]) / 20
                 last = sum(o.loss for o in outs[-20:]) / 20
-                good = (len(outs) == total and gs == total and seqs == list(range(1, total + 1))
+                if fuse:
+                    good_fused = w.kernels_per_step == 2   # the head really ran inside the forward kernel
+                else:
+                    good_fused = True
+                good = (good_fused and len(outs) == total and gs == total and seqs == list(range(1, total + 1))
                         and last < first and all(o.loss == o.loss for o in outs))
                 print(f"[{'PASS' if good else 'FAIL'}] {name}: steps={len(outs)} global_step={gs} "
                       f"seqs unique={seqs == list(range(1, total + 1))} loss {first:.4f} -> {last:.4f}", flush=True)

@@ -386,7 +386,7 @@ class Worker:
             hb = lay.by_name[names[L - 2][1]]  # bias of the last hidden layer
             inbox_ptr = self.seg.addr("inbox") if cfg.push_mode == "mailbox" else 0
             gs_ptr = self.ps_segs[self.gs_owner].addr("ctrl", 4 * CTRL_GLOBAL_STEP) if cfg.push_mode == "atomic" else 0
-            plans.append(head_ops.head_plan(
+            head = head_ops.head_plan(
                 h_ptr=act[L - 1].data_ptr(), labels_ptr=yd.value,
                 w_last_ptr=self.ps_segs[wl.ps].addr("params", wl.offset * 4),
                 b_last_ptr=self.ps_segs[bl.ps].addr("params", bl.offset * 4),
@@ -398,7 +398,11 @@ class Worker:
                 off_w_last=wl.offset, off_b_last=bl.offset, off_b_hidden=hb.offset,
                 item_w_last_base=wl.item_base, item_b_last=bl.item_base, item_b_hidden_base=hb.item_base,
                 seq_ptr=seq_ptr, inbox_ptr=inbox_ptr, n_inbox=len(self.inbox_order), ps_global_step_ptr=gs_ptr,
-                nslots=cfg.nslots, ldh=act[L - 1].shape[1]))
+                nslots=cfg.nslots, ldh=act[L - 1].shape[1])
+            if cfg.fuse_head and L == 2 and plans[0].can_fuse_head(sizes[L - 1][0], spec.num_classes):
+                plans[0].fuse_head(head.params)      # the head runs as the tail of the forward GEMM's cluster
+            else:
+                plans.append(head)
             # ---- backward of the hidden layers: dX (+ bias-grad push) *before* dW (fused push) of the same layer:
             #      dX pulls W_l from the PS a second time, and the PS applies a pushed dW_l within microseconds,
             #      so pushing dW_l first would let this step's own update leak into its dX ----
