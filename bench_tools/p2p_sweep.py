@@ -14,7 +14,6 @@ Also measures the flag ping-pong latency between the ps GPU and worker 1.
 from __future__ import annotations
 
 import argparse
-import ctypes as C
 import json
 import os
 

@@ -20,12 +20,10 @@ from __future__ import annotations
 
 import argparse
 import sys
-import time
 from typing import List, Optional
 
 import torch
 
-from . import _native as N
 from .cluster import ClusterSpec, Rendezvous, default_device_index
 from .models import mlp
 from .parallel.config import EngineConfig, OptimizerConfig

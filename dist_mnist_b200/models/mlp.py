@@ -19,8 +19,8 @@ path of the CPU plumbing backend; it is *not* the GPU hot path (that is `ops/` +
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
-from typing import Dict, List, Sequence, Tuple
+from dataclasses import dataclass
+from typing import Dict, List, Tuple
 
 import torch
 

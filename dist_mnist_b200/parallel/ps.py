@@ -19,7 +19,6 @@ import threading
 import time
 from typing import Dict, List, Optional
 
-import torch
 
 from .. import _native as N
 from ..cluster import ClusterSpec, Rendezvous

@@ -17,7 +17,7 @@ from typing import Callable, Dict, List, Optional
 
 import torch
 
-from .cluster import ClusterSpec, Rendezvous
+from .cluster import ClusterSpec
 from .utils.metrics import TrainMetricsWriter
 from .models.mlp import MLPSpec
 from .parallel.config import EngineConfig, OptimizerConfig
@@ -92,7 +92,7 @@ class TrainLoopResult:
 def train_loop(worker: Worker, dataset: Dataset, train_steps: int = 4000, log_every: int = 100,
                checkpoint_dir: Optional[str] = None, save_checkpoint_secs: float = 600.0, seed: int = 0,
                chunk: int = 50, print_fn: Callable[[str], None] = print,
-               inject_fault_after: int = 0, metrics: Optional["TrainMetricsWriter"] = None) -> TrainLoopResult:
+               inject_fault_after: int = 0, metrics: Optional[TrainMetricsWriter] = None) -> TrainLoopResult:
     """The worker's `MonitoredTrainingSession` loop (DS:106-116).
 
     Runs until a step reports `global_step >= train_steps` (StopAtStepHook on the shared counter), printing
