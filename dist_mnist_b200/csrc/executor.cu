@@ -2,14 +2,18 @@
 //
 // The reference's hot loop is `next_batch(32)` + `sess.run([train_op, loss, global_step], feed_dict)`
 // (/root/reference/distributed_server-basic.py:110-113): a host-driven iteration that feeds a numpy batch,
-// runs the step and reads loss / global_step back. Here one training step is a CUDA graph (captured once
-// from the kernel launch plans); the executor pipelines  gather -> H2D copy (copy stream) -> graph launch
-// (compute stream) -> 16-byte D2H result  over a ring of slots, so step i+1's input transfer overlaps step
-// i's kernels and the host never blocks on the step it just submitted.
+// runs the step and reads loss / global_step back. Here one training step is a chain of kernels inside a CUDA
+// graph (captured once from the kernel launch plans); the executor pipelines  gather (helper threads) -> H2D
+// copy (copy stream) -> graph launch (run streams) -> result (written by the step's kernel straight into pinned
+// host memory)  over a ring of slots. `lanes` steps of the worker are in flight at once (asynchronous SGD); U
+// consecutive slots form a group whose steps are parallel chains of one graph, so the native loops pay one
+// packed input transfer and one graph launch per U steps, and the host never blocks on what it just submitted.
 //
 //   BatchLoader : TF `DataSet.next_batch` semantics (shuffle per epoch, sequential batches, epoch wrap)
-//                 over a host-resident dataset; gathers rows into a pinned staging buffer.
-//   Executor    : slot ring {device x/y, pinned staging, result, graph exec, events}; submit / result / run.
+//                 over a host-resident dataset; plan() draws the row indices (sequential), copy() moves the rows
+//                 (any thread).
+//   Executor    : slot ring {device x/y, pinned staging, pinned result, graph exec, events} + groups
+//                 {contiguous buffers, U-step graph, run stream}; submit / submit_group / result / run.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>

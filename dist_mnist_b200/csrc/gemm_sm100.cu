@@ -17,6 +17,12 @@
 //
 // Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer,
 // warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+//
+// Split-K (forward / dX, whose K loop is TMA-issue bound on one SM): the splits of a tile form a thread-block
+// cluster and reduce-scatter their partial accumulators through distributed shared memory (global-scratch
+// variants remain for tiles wider than 64 columns). Kernels of one training step are chained with programmatic
+// dependent launch (griddepcontrol). Optional: the classifier head as the tail of the forward cluster
+// (fused_head_tail, GemmParams::fuse_head — correct, currently slower than the separate head kernel).
 #include "common.cuh"
 #include "protocol.h"
 

@@ -7,11 +7,12 @@ Reference parity (`/root/reference/distributed_server-basic.py`):
   * DS:110-113  one step = pull variables, forward/backward on the worker, push gradients, PS applies Adam and
                 bumps `global_step`; the worker gets `loss` and `global_step` back. No locks, no barriers.
 
-GPU backend: a step is one CUDA graph of hand-written sm_100a kernels (see `ops/`): the forward GEMMs pull
-their weight tiles straight out of the PS shard's HBM with TMA over NVLink, the dW GEMM epilogues and the
-classifier-head kernel push gradients into the PS mailbox (or red.add them into the master copy for SGD) and
-publish per-tile flags; the persistent PS kernel applies. The native executor pipelines H2D input copies,
-graph launches and the 16-byte result read-back (csrc/executor.cu).
+GPU backend: a step is a PDL-linked chain of hand-written sm_100a kernels inside a CUDA graph (see `ops/`): the
+forward GEMMs pull their weight tiles straight out of the PS shard's HBM with TMA over NVLink, the dW GEMM
+epilogues and the classifier-head kernel push gradients into the PS mailbox (or red.add them into the master
+copy for SGD) and publish per-tile flags; the persistent PS kernel applies. The native executor keeps
+`cfg.lanes` steps in flight, launches `cfg.graph_steps` of them per graph, gathers batches on helper threads
+and receives each step's 16-byte result in pinned host memory (csrc/executor.cu).
 
 CPU backend: same protocol over POSIX shm with torch CPU math (BASELINE.json config 1, plumbing tests).
 """
