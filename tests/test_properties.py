@@ -1,0 +1,70 @@
+"""Property tests (hypothesis): arena layout / item tiling for arbitrary MLP shapes, and the native next_batch
+loader against an independent model of TF's `DataSet.next_batch` for arbitrary dataset / batch sizes."""
+import torch
+from hypothesis import given, settings, strategies as st
+
+from dist_mnist_b200 import _native as N
+from dist_mnist_b200.models.mlp import MLPSpec
+from dist_mnist_b200.parallel import sharding
+
+
+@settings(max_examples=40, deadline=None)
+@given(in_features=st.integers(1, 300), hidden=st.lists(st.integers(1, 300), min_size=1, max_size=3),
+       classes=st.integers(2, 16), num_ps=st.integers(1, 4), strategy=st.sampled_from(["round_robin", "byte_balanced"]),
+       tile_n=st.sampled_from([32, 64]))
+def test_items_tile_any_model_exactly_once(in_features, hidden, classes, num_ps, strategy, tile_n):
+    spec = MLPSpec(name="prop", in_features=in_features, hidden=tuple(hidden), num_classes=classes, loss="xent",
+                   init="glorot")
+    lay = sharding.build_layout(spec, num_ps, strategy, dw_tile_n=tile_n)
+    assert set(lay.placement.values()) <= set(range(num_ps))
+    seen = 0
+    for sh in lay.shards:
+        cover = torch.zeros(sh.arena_elems, dtype=torch.int32)
+        for it in sh.items:
+            assert it.rows >= 1 and 1 <= it.cols <= max(sharding.TILE_M, tile_n)
+            for r in range(it.rows):
+                cover[it.offset + r * it.ld: it.offset + r * it.ld + it.cols] += 1
+        assert int(cover.max()) <= 1                      # no element belongs to two items
+        n_var_elems = 0
+        for vl in sh.variables:
+            assert vl.offset % sharding.ALIGN_ELEMS == 0  # TMA / float4 alignment of every variable
+            n_var_elems += vl.spec.numel
+            # flag indices of a variable are contiguous and inside the shard's item table
+            assert 0 <= vl.item_base and vl.item_base + vl.n_items <= sh.n_items
+        assert int(cover.sum()) == n_var_elems            # ... and every parameter belongs to exactly one
+        seen += len(sh.variables)
+    assert seen == 2 * (len(hidden) + 1)                  # one weight + one bias per layer, each placed once
+
+
+@settings(max_examples=30, deadline=None)
+@given(n=st.integers(1, 40), batch=st.integers(1, 17), n_batches=st.integers(1, 12), seed=st.integers(0, 2 ** 31),
+       shuffle=st.booleans())
+def test_native_loader_visits_every_sample_once_per_epoch(n, batch, n_batches, seed, shuffle):
+    """TF next_batch semantics: consecutive batches walk through a per-epoch permutation; a batch that crosses the
+    epoch boundary is completed from the next epoch; without shuffling the order is the dataset order."""
+    lib = N.lib()
+    pix, classes = 3, 2
+    x = torch.arange(n * pix, dtype=torch.float32).view(n, pix).contiguous()
+    y = torch.zeros(n, classes)
+    y[torch.arange(n), torch.arange(n) % classes] = 1
+    h = lib.dm_loader_create(x.data_ptr(), y.data_ptr(), n, pix * 4, classes * 4, pix * 4, classes * 4, batch, seed,
+                             int(shuffle))
+    xb, yb = torch.zeros(batch, pix), torch.zeros(batch, classes)
+    order = []
+    for _ in range(n_batches):
+        lib.dm_loader_next(h, xb.data_ptr(), yb.data_ptr())
+        idx = [int(v) // pix for v in xb[:, 0].tolist()]
+        for r, i in enumerate(idx):
+            assert torch.equal(xb[r], x[i]) and torch.equal(yb[r], y[i])
+        order += idx
+    total = n_batches * batch
+    for e in range(0, total, n):                          # every complete epoch is a permutation of the dataset
+        chunk = order[e: e + n]
+        if len(chunk) == n:
+            assert sorted(chunk) == list(range(n))
+        else:
+            assert len(set(chunk)) == len(chunk)          # the partial last epoch has no repeats
+    if not shuffle:
+        assert order == [i % n for i in range(total)]
+    assert lib.dm_loader_epochs(h) == (total - 1) // n     # the wrap happens lazily, when the next sample is needed
+    lib.dm_loader_destroy(h)
