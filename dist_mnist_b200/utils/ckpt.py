@@ -36,6 +36,7 @@ def save_checkpoint(worker, directory: str) -> str:
         "item_state": {k: worker.read_item_state(k) for k in range(worker.cluster.num_ps)},
         "sharding": worker.cfg.sharding,
         "num_ps": worker.cluster.num_ps,
+        "dw_tile_n": worker.layout.dw_tile_n,    # item tables (hence item_state) depend on the dW tile width
     }
     name = f"model.ckpt-{gstep}.pt"
     path = os.path.join(directory, name)
@@ -75,7 +76,11 @@ def restore_latest(worker, directory: Optional[str]) -> Optional[int]:
     worker.write_variables(state["variables"], "params")
     worker.write_variables(state["adam_m"], "adam_m")
     worker.write_variables(state["adam_v"], "adam_v")
-    if state.get("num_ps") == worker.cluster.num_ps and state.get("sharding") == worker.cfg.sharding:
+    # per-item optimizer state (Adam step count / beta powers) is only meaningful for the same item table; with a
+    # different shard count, placement or dW tile width the variables and Adam slots are restored and the
+    # per-item step counters restart (bias correction re-warms, as after a TF slot-variable reset)
+    if (state.get("num_ps") == worker.cluster.num_ps and state.get("sharding") == worker.cfg.sharding
+            and state.get("dw_tile_n", 64) == worker.layout.dw_tile_n):
         for k, st in state["item_state"].items():
             worker.write_item_state(int(k), st)
     worker.write_global_step(int(state["global_step"]))
