@@ -80,6 +80,8 @@ class ParameterServer:
         self._cpu_table = (C.c_void_p * N.MAX_WORKERS)() if cfg.backend == "cpu" else None
         self._lock = threading.Lock()
         self._dead = set()          # workers declared dead by the failure detector
+        self._incarnation: Dict[int, int] = {}   # worker -> incarnation number currently attached
+        self._readmit_restart = False
 
         kind = "cuda" if cfg.backend == "cuda" else "shm"
         if kind == "cuda":
@@ -204,21 +206,56 @@ class ParameterServer:
         new = []
         with self._lock:
             for w in range(self.n_workers):
-                if w in self._attached:
+                if w in self._attached and self.rdv.add(f"worker/{w}/incarnation", 0) == self._incarnation.get(w):
                     continue
                 desc = self.rdv.try_get(f"worker/{w}/inbox")
-                if desc is None:
+                if desc is None or desc.get("incarnation", 1) == self._incarnation.get(w):
                     continue
+                if w in self._attached:
+                    self._readmit(w)       # a restarted worker: forget everything about its previous life
                 seg = Segment.open(desc, device=self.device)
                 self._attached[w] = seg
+                self._incarnation[w] = desc.get("incarnation", 1)
                 self._attached_devices.append(desc.get("worker_device", -1))
                 ptr = seg.addr("inbox", 8 * desc["inbox_index"][str(self.task_index)]) \
                     if str(self.task_index) in desc["inbox_index"] else 0
                 if ptr:
                     self._patch_table(w, ptr)
-                self.rdv.put(f"ps/{self.task_index}/attached/{w}", True)
+                if self._readmit_restart:
+                    self._readmit_restart = False
+                    self.restart()
+                self.rdv.put(f"ps/{self.task_index}/attached/{w}/{self._incarnation[w]}", True)
                 new.append(w)
         return new
+
+    def _readmit(self, w: int) -> None:
+        """Elastic recovery: worker `w` crashed and was started again. Its new life begins with push sequence 1 and
+        a new inbox, so this shard drops the old incarnation's bookkeeping: the serve kernel is stopped (its
+        per-worker cursors live in shared memory), flags / consumed counters / cursors / the done word of `w` are
+        reset, and serving resumes. Parameters, optimizer state and global_step are untouched."""
+        print(f"[ps {self.task_index}] worker {w} re-registered (incarnation "
+              f"{self.rdv.add(f'worker/{w}/incarnation', 0)}): re-admitting it", flush=True)
+        old = self._attached.pop(w)
+        try:
+            old.close()
+        except Exception:
+            pass               # the process that exported it is gone
+        if self.cfg.push_mode == "atomic":
+            if w in self._dead and self.task_index == 0:
+                self.rdv.add("session/workers_done", -1)
+            self._dead.discard(w)
+            return
+        was_serving = self._serving
+        if was_serving:
+            self.stop()
+        ni, ns = max(self.shard.n_items, 1), self.cfg.nslots
+        self._host_write("flags", bytes(4 * ns * ni), 4 * w * ns * ni)
+        self._host_write("consumed", bytes(4 * ns), 4 * w * ns)
+        self._host_write("next_seq", bytes((C.c_uint32 * ni)(*([1] * ni))), 4 * w * ni)
+        self._host_write("ctrl", bytes(4), 4 * (CTRL_WORKER_DONE + w))
+        self._patch_table(w, 0)
+        self._dead.discard(w)
+        self._readmit_restart = was_serving
 
     # ------------------------------------------------------------------------------------------
     def kernel_running(self) -> bool:

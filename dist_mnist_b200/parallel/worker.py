@@ -140,6 +140,10 @@ class Worker:
         desc = self.seg.export()
         desc["inbox_index"] = {str(k): i for k, i in self.inbox_index.items()}
         desc["worker_device"] = self.device
+        # a worker that is restarted after a crash registers again under the next incarnation number; the ps
+        # tasks then re-admit it (fresh push sequence, fresh inbox) — the reference's recoverable session
+        self.incarnation = self.rdv.add(f"worker/{self.task_index}/incarnation", 1)
+        desc["incarnation"] = self.incarnation
         self.rdv.put(f"worker/{self.task_index}/inbox", desc)
         self.heartbeat()
         self._connected = True
@@ -149,7 +153,7 @@ class Worker:
         self.rdv.get("init/done", timeout_s)
         for k in range(self.cluster.num_ps):
             self.rdv.get(f"ps/{k}/serving", timeout_s)
-            self.rdv.get(f"ps/{k}/attached/{self.task_index}", timeout_s)
+            self.rdv.get(f"ps/{k}/attached/{self.task_index}/{self.incarnation}", timeout_s)
         self.prepare()
         # seed our view of the shared step counter (a restored session does not start at 0)
         g0 = self.read_global_step()

@@ -107,3 +107,29 @@ def test_worker_crash_is_detected_and_training_continues():
     outp = _finish(ps, 60)
     assert ps.returncode == 0, outp
     assert "worker 1 presumed dead" in outp, outp
+
+
+@pytest.mark.timeout(300)
+def test_crashed_worker_can_be_restarted_and_rejoins():
+    """Elastic recovery (the reference's `_RecoverableSession`): worker 1 crashes, is started
+    again with the same task index, the ps re-admits it (new incarnation: fresh push sequence and inbox) and it
+    trains on with worker 0 until the shared global step reaches the target."""
+    ps_hosts = f"127.0.0.1:{_free_port()}"
+    worker_hosts = f"127.0.0.1:{_free_port()},127.0.0.1:{_free_port()}"
+    common = ["--train_steps", "2500", "--learning_rate", "0.001", "--log_every", "500"]
+    ps = _spawn("ps", 0, ps_hosts, worker_hosts, common + ["--ps_exit_when_done", "--worker_timeout", "30"])
+    w0 = _spawn("worker", 0, ps_hosts, worker_hosts, common)
+    w1 = _spawn("worker", 1, ps_hosts, worker_hosts, common + ["--inject_fault", "30"])
+    out1 = _finish(w1, 120)
+    assert w1.returncode == 42, out1
+    w1b = _spawn("worker", 1, ps_hosts, worker_hosts, common + ["--metrics_file", os.devnull, "--log_steps_per_sec"])
+    out1b = _finish(w1b, 200)
+    out0 = _finish(w0, 200)
+    outp = _finish(ps, 60)
+    assert w1b.returncode == 0, out1b
+    assert w0.returncode == 0, out0
+    assert ps.returncode == 0, outp
+    assert "worker 1 re-registered (incarnation 2): re-admitting it" in outp, outp
+    # the restarted worker really trained: it reported steps of its own
+    assert "INFO global_step/sec" in out1b, out1b
+    assert "Train step 2500, loss:" in (out0 + out1b) or "Train step 2000, loss:" in (out0 + out1b)
