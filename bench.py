@@ -9,20 +9,20 @@ N >= 2 -> rank 0 is the dedicated ps GPU, ranks 1..N-1 are workers (N = 8 -> "1 
 Model/config: the reference's live model (784-100-10 "book" MLP, batch 32 per worker, Adam lr 1e-4,
 asynchronous per-push apply on the ps) with synthetic 28x28 data and random-init weights.
 
-Two numbers are reported (see the JSON keys):
-  value : K steps per worker, inputs streamed from a device-resident 55 000-image dataset (172 MB > L2),
-          timed with CUDA events on the worker's first run stream; the timed region opens with a fork to the other
-          run streams and ends with a stream-ordered join + wait for the PS acknowledgement of the last push, so
-          every step's kernels and optimizer applies are inside it.
-  e2e   : the same K steps through the public API (`Worker.run_steps`): native next_batch gather into pinned
-          memory, H2D copy of every batch, step graph, 16-byte result D2H per step; wall clock between
-          device synchronisations.
-Both take the max over ranks; throughput = (workers x K) / max elapsed.
+Numbers in the JSON line (all: max over ranks, throughput = workers x K / max elapsed):
+  value    : K steps per worker, inputs read from a device-resident 55 000-image dataset (172 MB > L2) — with the
+             fused engine ONE kernel launch whose TMA loads take the batch rows straight out of the dataset —
+             timed with CUDA events on the worker's compute stream; the region ends with a stream-ordered wait for
+             the ps acknowledgement of the last push, so every step's pull, math, push and optimizer apply is inside.
+  e2e      : the same K steps through the public API (`Worker.run_steps`): native next_batch gather into pinned
+             memory, H2D copy of every batch, step kernels, 16-byte result read back per step; wall clock between
+             device synchronisations, closed by the ps acknowledgement of the last push.
+  parity   : the reference's worker semantics — one step at a time per worker (`--lanes 1`), host-fed — and the same
+             with `--strict_steps` (the next pull waits for the acknowledgement of the previous push).
+  roofline : achieved fraction of the NVLink / HBM / tensor-core rooflines from MEASURED_PEAKS.json.
 
-Steps in flight: a worker keeps `--lanes` (default 8) consecutive steps in flight on its GPU — asynchronous SGD,
-every step still pulls, computes, pushes and is applied on the ps individually (`gpu_launches` counts every kernel
-of every step); the native loops issue `--graph_steps` (default 4) steps per CUDA-graph launch. `--lanes 1` gives
-the strictly sequential per-worker loop of the reference. The JSON `config` records all three knobs.
+Steps in flight: a worker keeps `--lanes` (default 8, the CLI's default too) steps in flight on its GPU — bounded-
+staleness asynchronous SGD: every step still pulls, computes, pushes and is applied on the ps individually.
 """
 from __future__ import annotations
 
@@ -40,6 +40,7 @@ REFERENCE_UNAVAILABLE = (
     "/opt/wheelhouse, none for Python 3.12, no network; /root/reference has no setup.py/pyproject so "
     "`pip install --target baseline/_ref /root/reference` fails with 'not installable'"
 )
+NVLINK_GBS = 770.0   # measured peer-copy bandwidth per direction per GPU (profiling recipe)
 
 
 def parse_args(argv=None):
@@ -57,14 +58,39 @@ def parse_args(argv=None):
     p.add_argument("--push_mode", choices=["mailbox", "atomic"], default="mailbox")
     p.add_argument("--apply_mode", choices=["per_push", "merged"], default="per_push")
     p.add_argument("--num_ps", type=int, default=1)
-    p.add_argument("--sharding", choices=["round_robin", "byte_balanced"], default="round_robin")
-    p.add_argument("--nslots", type=int, default=0, help="mailbox slots per worker (0 = max(2, lanes))")
+    p.add_argument("--sharding", choices=["round_robin", "byte_balanced", "row_split"], default="round_robin")
+    p.add_argument("--engine", choices=["auto", "fused", "graph"], default="auto")
+    p.add_argument("--nslots", type=int, default=0, help="mailbox slots per worker (0 = 2 x lanes)")
     p.add_argument("--lanes", type=int, default=8,
                    help="steps of one worker in flight on its GPU at once (async SGD; must be <= nslots)")
+    p.add_argument("--strict_steps", action="store_true")
     p.add_argument("--graph_steps", type=int, default=0,
-                   help="steps per CUDA-graph launch in the native loops (0 = min(lanes, 4))")
+                   help="graph engine: steps per CUDA-graph launch in the native loops (0 = min(lanes, 4))")
+    p.add_argument("--ps_row_blocks", type=int, default=4)
     p.add_argument("--skip_e2e", action="store_true")
+    p.add_argument("--skip_parity", action="store_true")
     return p.parse_args(argv)
+
+
+def engine_config(args, backend: str = "cuda"):
+    """Same derivation as `dist_mnist_b200.cli.engine_config_from_args` (tests compare the two)."""
+    from dist_mnist_b200.parallel.config import EngineConfig
+
+    lanes = max(1, args.lanes)
+    return EngineConfig(backend=backend, dtype=args.dtype, nslots=args.nslots or 2 * lanes, apply_mode=args.apply_mode,
+                        push_mode=args.push_mode, sharding=args.sharding, lanes=lanes,
+                        graph_steps=args.graph_steps or min(lanes, 4), pipeline_slots=max(4, 2 * lanes),
+                        engine=args.engine, strict_steps=args.strict_steps, ps_row_blocks=args.ps_row_blocks)
+
+
+def load_peaks() -> dict:
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]), "source": "MEASURED_PEAKS.json"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (profiling recipe)"}
 
 
 def main(argv=None) -> int:
@@ -78,7 +104,7 @@ def main(argv=None) -> int:
     from dist_mnist_b200 import _native as N
     from dist_mnist_b200.cluster import ClusterSpec, Rendezvous
     from dist_mnist_b200.models import mlp
-    from dist_mnist_b200.parallel.config import EngineConfig, OptimizerConfig
+    from dist_mnist_b200.parallel.config import OptimizerConfig
     from dist_mnist_b200.parallel.ps import ParameterServer
     from dist_mnist_b200.parallel.worker import Worker
     from dist_mnist_b200.session import InProcessCluster
@@ -104,19 +130,15 @@ def main(argv=None) -> int:
 
     spec = mlp.get_model(args.model, args.hidden_units)
     opt = OptimizerConfig(args.optimizer, args.learning_rate)
-    args.nslots = args.nslots or max(2, args.lanes)
-    args.graph_steps = args.graph_steps or min(args.lanes, 4)
-    cfg = EngineConfig(backend="cuda", dtype=args.dtype, nslots=args.nslots, apply_mode=args.apply_mode,
-                       push_mode=args.push_mode, sharding=args.sharding, lanes=args.lanes,
-                       graph_steps=args.graph_steps, pipeline_slots=max(4, 2 * args.lanes))
+    cfg = engine_config(args)
     cfg.validate(opt)
-    K, W, B = args.steps, args.warmup, args.batch_size
+    engine = cfg.resolve_engine(spec, args.batch_size)
+    K, W, B = args.steps, max(args.warmup, 3), args.batch_size
 
     # ---------------- data (allocated before any persistent PS kernel exists on this GPU) ----------------
     ds = data_utils.synthetic_mnist(data_utils.TRAIN_SIZE, seed=0)
     is_worker_rank = world == 1 or rank >= args.num_ps
     dev_x = dev_y = None
-    pin_x = pin_y = None
     if is_worker_rank:
         dev = torch.device("cuda", local_rank)
         tdtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
@@ -147,7 +169,7 @@ def main(argv=None) -> int:
                               tuple(f"{addr}:{port + 200 + i}" for i in range(n_workers)))
         if rank < num_ps:
             rdv = Rendezvous(cluster, "ps", rank)
-            ps = ParameterServer(cluster, rank, spec, opt, cfg, device=local_rank, rdv=rdv)
+            ps = ParameterServer(cluster, rank, spec, opt, cfg, device=local_rank, rdv=rdv, batch_size=B)
             ps.start()
             # workers register in any order; keep attaching (what `ps.join()` does in the CLI) until all are in
             t_att = time.time()
@@ -203,58 +225,91 @@ def main(argv=None) -> int:
                     rdv_any.add(f"bench/{ph}/serving", 1)
                 rdv_any.wait_count(f"bench/{ph}/serving", args.num_ps)
 
-    elapsed_ms = 0.0
-    host_enqueue_ms = 0.0
-    e2e_s = 0.0
-    h2d_bytes = d2h_bytes = 0
+    n_rows = xrow = yrow = 0
     if worker is not None:
         assert worker.ld_in == dev_x.shape[1]
         n_rows = dev_x.shape[0] - worker.B_pad
         xrow, yrow = dev_x.shape[1] * dev_x.element_size(), dev_y.shape[1] * 4
+    cursor = [0]
 
-        def resident_steps(n, start):
-            worker.run_resident(n, dev_x.data_ptr(), dev_y.data_ptr(), xrow, yrow, n_rows, start)
+    def resident_steps(n):
+        worker.run_resident(n, dev_x.data_ptr(), dev_y.data_ptr(), xrow, yrow, n_rows, cursor[0])
+        cursor[0] += n
 
-        resident_steps(max(W, 3), 0)
-        loader = loaders["l"]
+    def device_timed(n):
+        """n steps, CUDA-event timed on the compute stream incl. the ps acknowledgement of the last push (ms)."""
+        timer = StreamTimer(worker.compute_stream, local_rank)
+        timer.start()
+        worker.fork_lanes()   # graph engine: no lane starts a timed step before the start event
+        t_host = time.perf_counter()
+        resident_steps(n)
+        enq_ms = (time.perf_counter() - t_host) * 1e3
+        worker.enqueue_wait_ack()
+        timer.stop()
+        return timer.elapsed_ms(), enq_ms
 
+    def host_fed(n):
+        """n steps through Worker.run_steps (gather + H2D + kernels + result read-back), wall clock (s)."""
+        t0 = time.perf_counter()
+        outs = worker.run_steps(n, loaders["l"])   # returns when every result has been read back
+        worker.wait_applied()                       # ... and every push of the region is applied on the ps
+        dt = time.perf_counter() - t0
+        assert len(outs) == n, (len(outs), n)
+        return dt
+
+    elapsed_ms = host_enqueue_ms = e2e_s = 0.0
+    par = {"dev_ms": 0.0, "e2e_s": 0.0, "strict_ms": 0.0}
+    h2d_bytes = d2h_bytes = 0
+    launches = 0
+    if worker is not None:
+        resident_steps(W)
     sampler = ClockSampler(interval_ms=100, gpu_indices=list(range(n_gpus))) if rank == 0 else None
     full_sync()
     if sampler:
         sampler.start()
 
     # ---------------- timed region 1: device-timed steps ----------------
-    launches_before = worker.kernel_launches() if worker is not None else 0
     if worker is not None:
-        timer = StreamTimer(worker.compute_stream, local_rank)
-        timer.start()
-        worker.fork_lanes()   # no lane starts a timed step before the start event
-        t_host = time.perf_counter()
-        resident_steps(K, max(W, 3))
-        host_enqueue_ms = (time.perf_counter() - t_host) * 1e3
-        worker.enqueue_wait_ack()
-        timer.stop()
-        elapsed_ms = timer.elapsed_ms()
+        launches_before = worker.kernel_launches()
+        elapsed_ms, host_enqueue_ms = device_timed(K)
+        launches = worker.kernel_launches() - launches_before + 1   # + the acknowledgement-wait kernel
     full_sync()
-    launches = (worker.kernel_launches() - launches_before + 1) if worker is not None else 0
 
     # ---------------- timed region 2: end to end through the public API ----------------
     if not args.skip_e2e:
         if worker is not None:
-            worker.run_steps(max(W, 3), loader)
+            worker.run_steps(W, loaders["l"])
         full_sync()
         if worker is not None:
-            t0 = time.perf_counter()
-            outs = worker.run_steps(K, loader)   # drains: every result has been read back on return
-            worker.wait_applied()                # ... and every push of the region is applied on the ps
-            e2e_s = time.perf_counter() - t0
-            assert len(outs) == K
+            e2e_s = host_fed(K)
             h2d_bytes = worker.x_bytes + worker.y_bytes
             d2h_bytes = C.sizeof(N.StepResult)
-    clocks_stop_needed = sampler is not None
+        full_sync()
+
+    # ---------------- reference-semantics lines: one step at a time per worker ----------------
+    do_parity = not args.skip_parity and engine == "fused" and args.lanes != 1
+    if do_parity:
+        if worker is not None:
+            worker.set_lanes(1, strict=False)
+            resident_steps(W)
+            worker.run_steps(W, loaders["l"])
+        full_sync()
+        if worker is not None:
+            par["dev_ms"], _ = device_timed(K)
+        full_sync()
+        if worker is not None:
+            par["e2e_s"] = host_fed(K)
+            worker.set_lanes(1, strict=True)
+            resident_steps(W)
+        full_sync()
+        if worker is not None:
+            par["strict_ms"], _ = device_timed(K)
+            worker.set_lanes(args.lanes, strict=args.strict_steps)
+        full_sync()
+
     final_step = worker.read_global_step() if (worker is not None and worker.is_chief) else 0
     full_sync(restart=False)   # serve kernels stay down from here on: torch/NCCL ops below are safe
-    clocks = sampler.stop() if clocks_stop_needed else None
+    clocks = sampler.stop() if sampler is not None else None
     for ps in ps_list:   # DM_PS_STATS=1: serve-kernel statistics of this rank's shard (diagnostics, stderr)
         st = ps.serve_stats()
         if st:
@@ -263,7 +318,8 @@ def main(argv=None) -> int:
     # ---------------- reduce over ranks ----------------
     kps = worker.kernels_per_step if worker is not None else 0
     stats = torch.tensor([elapsed_ms, e2e_s, float(launches), float(h2d_bytes), float(d2h_bytes), float(final_step),
-                          float(kps), host_enqueue_ms], dtype=torch.float64, device="cuda")
+                          float(kps), host_enqueue_ms, par["dev_ms"], par["e2e_s"], par["strict_ms"]],
+                         dtype=torch.float64, device="cuda")
     mx = stats.clone()
     sm = stats.clone()
     if world > 1:
@@ -274,13 +330,30 @@ def main(argv=None) -> int:
         max_ms, max_e2e = float(mx[0]), float(mx[1])
         value = n_workers * K / (max_ms / 1e3)
         n_params = spec.num_params
+        peaks = load_peaks()
+        # per step: the parameters cross NVLink once in each direction (pull + push), the ps reads the pushed
+        # gradient and reads + writes params / m / v (7 x params bytes of HBM/L2 traffic), 2 x fwd + bwd FLOPs
+        pbytes = n_params * 4
+        flops_step = sum(2 * 2 * B * fi * fo for fi, fo in spec.layer_sizes) + 2 * B * sum(
+            fi * fo for fi, fo in spec.layer_sizes[1:])
+        per_worker = value / n_workers
+        roof = {
+            "nvlink_frac": (round(value * pbytes / (NVLINK_GBS * 1e9), 4) if world > 1 else None),
+            "nvlink_note": "ps port, each direction: value x param bytes / 770 GB/s (measured peer copy)",
+            "hbm_frac": round(value * 7 * pbytes / (peaks["hbm_gbs"] * 1e9), 4),
+            "hbm_note": "ps GPU: value x 7 x param bytes (g read, p/m/v read+write) / measured HBM copy bandwidth",
+            "tensor_frac": round(per_worker * flops_step / (peaks["bf16_tflops"] * 0.5 * 1e12), 6),
+            "tensor_note": "per worker GPU: steps/s x FLOPs/step / (0.5 x measured bf16 peak = tf32 rate)",
+            "peaks": peaks,
+            "bound": "latency (dependent phases of a 10 MFLOP / 0.64 MB step), not bytes or FLOPs",
+        }
         out = {
             "metric": "MNIST-MLP steps/sec (whole box, device-timed, max over ranks)",
             "value": value,
             "unit": "steps/s",
             "n_gpus": n_gpus,
             "steps": K,
-            "warmup": max(W, 3),
+            "warmup": W,
             "ms_per_step": max_ms / K,
             "higher_is_better": True,
             "scaling": "weak",
@@ -296,9 +369,11 @@ def main(argv=None) -> int:
                                 + (" (ps and worker share the GPU)" if world == 1 else " (dedicated ps GPU)")),
                 "optimizer": f"{args.optimizer} lr={args.learning_rate}",
                 "apply": f"{args.push_mode}/{args.apply_mode}",
+                "engine": engine,
+                "sharding": args.sharding,
                 "steps_in_flight_per_worker": args.lanes,
-                "steps_per_graph_launch": args.graph_steps,
-                "mailbox_slots": args.nslots,
+                "strict_steps": bool(args.strict_steps),
+                "mailbox_slots": cfg.nslots,
                 "host_enqueue_us_per_step": round(float(mx[7]) * 1e3 / K, 2),
                 "l2_policy": "inputs stream from a 55000x784 device-resident dataset (172 MB fp32 > 126 MB L2); "
                              "parameters (0.3 MB) stay L2-resident as in real training",
@@ -307,6 +382,8 @@ def main(argv=None) -> int:
             "clocks": clocks,
             "gpu_launches": int(sm[2]),
             "kernels_per_step": int(mx[6]),
+            "steps_per_launch": (K if engine == "fused" else cfg.graph_steps),
+            "roofline": roof,
             "impl": "ours",
         }
         if not args.skip_e2e:
@@ -317,6 +394,16 @@ def main(argv=None) -> int:
                 "h2d_bytes_per_step": int(mx[3]),
                 "d2h_bytes_per_step": int(mx[4]),
                 "timing": "wall clock between device synchronisations, max over ranks",
+            }
+        if do_parity:
+            out["parity"] = {
+                "what": "reference worker semantics: one step at a time per worker (--lanes 1)",
+                "value_device_timed": n_workers * K / (float(mx[8]) / 1e3),
+                "value_host_fed": n_workers * K / float(mx[9]),
+                "value_strict_device_timed": n_workers * K / (float(mx[10]) / 1e3),
+                "strict": "--strict_steps: the next pull waits for the ps acknowledgement of the previous push "
+                          "(sess.run returns after the apply, reference DS:110-113)",
+                "unit": "steps/s",
             }
         print(json.dumps(out), flush=True)
 

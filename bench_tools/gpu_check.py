@@ -260,11 +260,12 @@ def check_ps_serve() -> bool:
         stop = torch.zeros(1, dtype=torch.int32, device=dev)
         exitc = torch.zeros(1, dtype=torch.int32, device=dev)
         inbox = torch.zeros(n_workers, 2, dtype=torch.int32, device=dev)
-        items_t = torch.zeros(n_items, 6, dtype=torch.int32, device=dev)
+        items_t = torch.zeros(n_items, C.sizeof(N.PsItem) // 4, dtype=torch.int32, device=dev)
         host_items = (N.PsItem * n_items)()
         for i, (off, r, c, l) in enumerate(items):
             host_items[i].offset, host_items[i].rows, host_items[i].cols, host_items[i].ld = off, r, c, l
             host_items[i].flags = 1
+            host_items[i].flag_index = i
         items_t.view(torch.uint8).view(-1).copy_(torch.frombuffer(bytearray(bytes(host_items)), dtype=torch.uint8).cuda())
         state = torch.zeros(n_items, 4, dtype=torch.int32, device=dev)
         st_host = (N.PsItemState * n_items)()
@@ -282,6 +283,7 @@ def check_ps_serve() -> bool:
         P.params, P.adam_m, P.adam_v, P.shadow_bf16 = params.data_ptr(), m.data_ptr(), v.data_ptr(), shadow.data_ptr()
         P.items, P.item_state = items_t.data_ptr(), state.data_ptr()
         P.n_items, P.n_workers, P.nslots, P.opt, P.apply_mode = n_items, n_workers, nslots, opt, apply_mode
+        P.n_flags = n_items
         P.lr, P.beta1, P.beta2, P.eps = 1e-2, 0.9, 0.999, 1e-8
         P.mailbox, P.arena_elems = mailbox.data_ptr(), arena
         P.flags, P.next_seq, P.consumed = flags.data_ptr(), next_seq.data_ptr(), consumed.data_ptr()

@@ -135,6 +135,7 @@ def main() -> int:
     for i, it in enumerate(sh.items):
         items[i].offset, items[i].rows, items[i].cols, items[i].ld = it.offset, it.rows, it.cols, it.ld
         items[i].flags = 1 if (it.shadow and dt == N.DT_BF16) else 0
+        items[i].flag_index = i
     items_t = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).cuda()
     st = (N.PsItemState * n_items)()
     for i in range(n_items):
@@ -150,6 +151,7 @@ def main() -> int:
     P.shadow_bf16 = shadow.data_ptr() if dt == N.DT_BF16 else None
     P.items, P.item_state = items_t.data_ptr(), state_t.data_ptr()
     P.n_items, P.n_workers, P.nslots = n_items, 1, nslots
+    P.n_flags = n_items
     P.opt, P.apply_mode = (N.OPT_ADAM if args.opt == "adam" else N.OPT_SGD), N.APPLY_PER_PUSH
     P.lr, P.beta1, P.beta2, P.eps = 1e-4, 0.9, 0.999, 1e-8
     P.mailbox, P.arena_elems = mailbox.data_ptr(), arena

@@ -87,7 +87,8 @@ class HeadParams(C.Structure):
 
 
 class PsItem(C.Structure):
-    _fields_ = [("offset", C.c_uint64), ("rows", C.c_int), ("cols", C.c_int), ("ld", C.c_int), ("flags", C.c_int)]
+    _fields_ = [("offset", C.c_uint64), ("rows", C.c_int), ("cols", C.c_int), ("ld", C.c_int), ("flags", C.c_int),
+                ("flag_index", C.c_int), ("pad_", C.c_int)]
 
 
 class PsItemState(C.Structure):
@@ -98,7 +99,8 @@ class PsServeParams(C.Structure):
     _fields_ = [
         ("params", C.c_void_p), ("adam_m", C.c_void_p), ("adam_v", C.c_void_p), ("shadow_bf16", C.c_void_p),
         ("items", C.c_void_p), ("item_state", C.c_void_p),
-        ("n_items", C.c_int), ("n_workers", C.c_int), ("nslots", C.c_int), ("opt", C.c_int), ("apply_mode", C.c_int),
+        ("n_items", C.c_int), ("n_flags", C.c_int), ("n_workers", C.c_int), ("nslots", C.c_int), ("opt", C.c_int),
+        ("apply_mode", C.c_int),
         ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
         ("mailbox", C.c_void_p), ("arena_elems", C.c_uint64),
         ("flags", C.c_void_p), ("next_seq", C.c_void_p), ("consumed", C.c_void_p),
@@ -106,13 +108,54 @@ class PsServeParams(C.Structure):
         ("inbox_table", C.c_void_p),
         ("exit_counter", C.c_void_p),
         ("gpu_scope", C.c_uint32), ("lookahead", C.c_uint32),
+        ("oneshot", C.c_uint32), ("pad2_", C.c_uint32),
         ("stats", C.c_void_p),
     ]
+
+
+FUSED_CLUSTER = 8
+FUSED_MAX_CHUNKS = 4
+FUSED_MAX_SHARDS = 8
+FUSED_ROWS_PER_SLOT = 32
+
+
+class FusedSlice(C.Structure):
+    _fields_ = [("kc_begin", C.c_int), ("kc_count", C.c_int), ("shard", C.c_int), ("flag_index", C.c_int),
+                ("w_offset", C.c_uint64)]
+
+
+class FusedShard(C.Structure):
+    _fields_ = [("push", PushTarget), ("inbox", C.c_void_p)]
+
+
+class FusedParams(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("H", C.c_int), ("C", C.c_int), ("I", C.c_int),
+        ("loss_kind", C.c_int), ("ldw", C.c_int), ("n_shards", C.c_int), ("strict", C.c_int),
+        ("slice", FusedSlice * FUSED_CLUSTER),
+        ("shard", FusedShard * FUSED_MAX_SHARDS),
+        ("bias_h", C.c_void_p), ("w_last", C.c_void_p), ("b_last", C.c_void_p),
+        ("shard_bh", C.c_int), ("shard_wl", C.c_int), ("shard_bl", C.c_int),
+        ("flag_bh", C.c_int), ("flag_wl", C.c_int), ("flag_bl", C.c_int),
+        ("off_bh", C.c_uint64), ("off_wl", C.c_uint64), ("off_bl", C.c_uint64),
+        ("y_base", C.c_void_p),
+        ("row_start", C.c_uint64), ("row_stride", C.c_uint64), ("row_wrap", C.c_uint64),
+        ("n_steps", C.c_uint32), ("seq_base", C.c_uint32), ("nslots", C.c_uint32), ("stop_at", C.c_uint32),
+        ("step_counter", C.c_void_p), ("stop_word", C.c_void_p), ("seq_word", C.c_void_p),
+        ("ps_global_step", C.c_void_p),
+        ("results", C.c_void_p),
+        ("debug_ts", C.c_void_p),
+    ]
+
+
+class FusedMaps(C.Structure):
+    _fields_ = [("w", (C.c_uint8 * 128) * FUSED_CLUSTER), ("xk", C.c_uint8 * 128), ("xmn", C.c_uint8 * 128)]
 
 
 _MIRRORS = {
     "PushTarget": PushTarget, "GemmParams": GemmParams, "HeadParams": HeadParams, "StepResult": StepResult,
     "PsItem": PsItem, "PsItemState": PsItemState, "PsServeParams": PsServeParams,
+    "FusedSlice": FusedSlice, "FusedShard": FusedShard, "FusedParams": FusedParams, "FusedMaps": FusedMaps,
 }
 
 WORKER_DEAD = 0xFFFFFFFF   # protocol.h kWorkerDead
@@ -140,6 +183,7 @@ def _declare(l: C.CDLL) -> None:
         "dm_set_device": (i, [i]),
         "dm_device_sm_count": (i, [i, C.POINTER(i)]),
         "dm_device_cc": (i, [i, C.POINTER(i), C.POINTER(i)]),
+        "dm_device_clock_khz": (i, [i, C.POINTER(i)]),
         "dm_cuda_malloc": (i, [i, sz, C.POINTER(vp)]),
         "dm_cuda_free": (i, [vp]),
         "dm_host_alloc": (i, [sz, C.POINTER(vp)]),
@@ -155,6 +199,7 @@ def _declare(l: C.CDLL) -> None:
         "dm_stream_destroy": (i, [vp]),
         "dm_stream_sync": (i, [vp]),
         "dm_stream_query": (i, [vp]),
+        "dm_stream_wait_stream": (i, [vp, vp]),
         "dm_make_tensor_map_2d": (i, [vp, vp, i, u64, u64, u64, u32, u32, i]),
         "dm_gemm_smem_bytes": (i, [i, i, i]),
         "dm_launch_gemm": (i, [vp, vp, vp, i, i, i, i, vp]),
@@ -210,6 +255,26 @@ def _declare(l: C.CDLL) -> None:
         "dm_exec_submitted": (u64, [vp]),
         "dm_exec_kernel_launches": (u64, [vp]),
         "dm_exec_destroy": (i, [vp]),
+        "dm_launch_fused": (i, [vp, vp, i, vp]),
+        "dm_fused_max_lanes": (i, [i, C.POINTER(i)]),
+        "dm_fused_smem_bytes": (i, []),
+        "dm_fexec_last_error": (C.c_char_p, []),
+        "dm_fexec_create": (i, [i, i, i, i, i, C.POINTER(vp)]),
+        "dm_fexec_buffers": (i, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
+                                 C.POINTER(i)]),
+        "dm_fexec_set_params": (i, [vp, vp, vp]),
+        "dm_fexec_compute_stream": (vp, [vp]),
+        "dm_fexec_steps_done": (u64, [vp]),
+        "dm_fexec_launches": (u64, [vp]),
+        "dm_fexec_lanes": (i, [vp]),
+        "dm_fexec_set_lanes": (i, [vp, i]),
+        "dm_fexec_gather_threads": (i, [vp]),
+        "dm_fexec_drain": (i, [vp]),
+        "dm_fexec_steps_host": (i, [vp, vp, vp, u32, vp, C.POINTER(u32)]),
+        "dm_fexec_run": (i, [vp, vp, u64, vp, u32, C.POINTER(u64)]),
+        "dm_fexec_run_resident": (i, [vp, vp, vp, u64, u64, u64, u64]),
+        "dm_fexec_resident_results": (i, [vp, vp, u64, C.POINTER(u64)]),
+        "dm_fexec_destroy": (i, [vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(l, name)
@@ -266,7 +331,8 @@ def available() -> bool:
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         l = lib()
-        msg = l.dm_last_error().decode() or l.dm_exec_last_error().decode() or l.dm_host_last_error().decode()
+        msg = (l.dm_last_error().decode() or l.dm_exec_last_error().decode() or l.dm_fexec_last_error().decode()
+               or l.dm_host_last_error().decode())
         raise NativeError(f"{what or 'native call'} failed (rc={rc}): {msg}")
 
 

@@ -35,6 +35,20 @@ from .utils import data as data_utils
 from .utils.metrics import TrainMetricsWriter
 
 
+DEFAULT_LANES = 8    # the engine's default (bench.py uses the same); --lanes 1 reproduces the reference's sequential loop
+
+
+def engine_config_from_args(args, backend: str) -> EngineConfig:
+    """The engine configuration every task derives from the command line (ps and worker tasks must agree)."""
+    lanes = max(1, args.lanes)
+    nslots = args.nslots or 2 * lanes
+    gsteps = args.graph_steps or min(lanes, 4)
+    return EngineConfig(backend=backend, dtype=args.dtype, nslots=nslots, apply_mode=args.apply_mode,
+                        push_mode=args.push_mode, sharding=args.sharding, colocate=args.colocate, lanes=lanes,
+                        graph_steps=gsteps, pipeline_slots=max(4, 2 * lanes), engine=args.engine,
+                        strict_steps=args.strict_steps, ps_row_blocks=args.ps_row_blocks)
+
+
 def build_parser() -> argparse.ArgumentParser:
     p = argparse.ArgumentParser(prog="distributed_server-basic", description=__doc__,
                                 formatter_class=argparse.RawDescriptionHelpFormatter)
@@ -57,13 +71,23 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--backend", choices=["auto", "cuda", "cpu"], default="auto")
     p.add_argument("--push_mode", choices=["mailbox", "atomic"], default="mailbox")
     p.add_argument("--apply_mode", choices=["per_push", "merged"], default="per_push")
-    p.add_argument("--sharding", choices=["round_robin", "byte_balanced"], default="round_robin")
-    p.add_argument("--nslots", type=int, default=2)
-    p.add_argument("--lanes", type=int, default=1,
-                   help="steps of this worker in flight at once (1 = like the reference: a step starts after the "
-                        "previous one's kernels; 2 overlaps consecutive steps, needs --nslots >= 2)")
-    p.add_argument("--graph_steps", type=int, default=1,
-                   help="steps per CUDA-graph launch in the native train loop (divides --lanes)")
+    p.add_argument("--sharding", choices=["round_robin", "byte_balanced", "row_split"], default="round_robin",
+                   help="variable -> ps placement: round_robin = the reference's replica_device_setter; row_split also "
+                        "splits the hidden weight along its input features over every ps task (fused engine)")
+    p.add_argument("--engine", choices=["auto", "fused", "graph"], default="auto",
+                   help="fused: one persistent kernel runs whole steps (784-H-10, H <= 128, batch <= 32, fp32); "
+                        "graph: per-layer kernels in a CUDA graph (any model / dtype)")
+    p.add_argument("--nslots", type=int, default=0, help="mailbox slots per worker (0 = 2 x lanes)")
+    p.add_argument("--lanes", type=int, default=DEFAULT_LANES,
+                   help="steps of this worker in flight at once: bounded-staleness asynchronous SGD inside one worker "
+                        "(1 = strictly one step after the other, like the reference's sess.run loop)")
+    p.add_argument("--strict_steps", action="store_true",
+                   help="fused engine: pull the weights of a lane's next step only after the ps acknowledged its "
+                        "previous push (with --lanes 1: exactly the reference's read-your-writes order)")
+    p.add_argument("--graph_steps", type=int, default=0,
+                   help="graph engine: steps per CUDA-graph launch in the native train loop (0 = min(lanes, 4))")
+    p.add_argument("--ps_row_blocks", type=int, default=4,
+                   help="fused tiling: ps items (serve-kernel CTAs) per pushed column slice of the hidden weight")
     p.add_argument("--checkpoint_dir", type=str, default=None, help="chief checkpoints here (default: mkdtemp, DS:106)")
     p.add_argument("--save_checkpoint_secs", type=float, default=600.0)
     p.add_argument("--gpu", type=int, default=None, help="CUDA device for this task (default: ps k -> k, worker i -> num_ps+i)")
@@ -114,9 +138,7 @@ def run(args: argparse.Namespace) -> int:
     backend = resolve_backend(args.backend)
     spec = mlp.get_model(args.model, args.hidden_units)
     opt = OptimizerConfig(args.optimizer, args.learning_rate)
-    cfg = EngineConfig(backend=backend, dtype=args.dtype, nslots=args.nslots, apply_mode=args.apply_mode,
-                       push_mode=args.push_mode, sharding=args.sharding, colocate=args.colocate, lanes=args.lanes,
-                       graph_steps=args.graph_steps, pipeline_slots=max(4, 2 * args.lanes))
+    cfg = engine_config_from_args(args, backend)
     cfg.validate(opt)
     device = -1
     if backend == "cuda":
@@ -126,7 +148,8 @@ def run(args: argparse.Namespace) -> int:
     rdv = Rendezvous(cluster, args.job_name, args.task_index, timeout_s=args.rendezvous_timeout)
 
     if args.job_name == "ps":
-        ps = ParameterServer(cluster, args.task_index, spec, opt, cfg, device=device, rdv=rdv)
+        ps = ParameterServer(cluster, args.task_index, spec, opt, cfg, device=device, rdv=rdv,
+                             batch_size=args.batch_size)
         ps.start()
         try:
             # DS:83 — blocks forever unless asked otherwise
@@ -141,11 +164,18 @@ def run(args: argparse.Namespace) -> int:
     dataset = data_utils.get_dataset(args.data_dir, seed=args.seed)  # DS:69 (every worker holds the full set)
     worker.connect()
     if worker.is_chief:
-        restored = ckpt_utils.restore_latest(worker, args.checkpoint_dir)
-        if restored is None:
-            worker.initialize_variables(seed=args.seed)
+        if worker.variables_are_live():
+            # a restarted chief (incarnation > 1): the ps tasks still hold the live training state the other workers
+            # keep updating — re-running the initialisers (or restoring an older checkpoint) would reset parameters
+            # and Adam slots under them while global_step and the per-item step counts keep running
+            print(f"[worker 0] restarted (incarnation {worker.incarnation}): variables are live on the ps, "
+                  f"not re-initialising", flush=True)
         else:
-            worker.mark_initialized()
+            restored = ckpt_utils.restore_latest(worker, args.checkpoint_dir)
+            if restored is None:
+                worker.initialize_variables(seed=args.seed)
+            else:
+                worker.mark_initialized()
     worker.wait_ready()
     metrics = None
     if args.metrics_file or args.log_steps_per_sec:

@@ -104,6 +104,7 @@ class Rendezvous:
         self.cluster = cluster
         self.is_master = job_name == "ps" and task_index == 0
         host, port = endpoint if endpoint is not None else cluster.rendezvous_endpoint()
+        self._endpoint = (host, port)
         self.timeout_s = timeout_s
         last_err: Optional[Exception] = None
         deadline = time.time() + timeout_s
@@ -120,6 +121,16 @@ class Rendezvous:
                 time.sleep(0.2)
         if self.store is None:
             raise TimeoutError(f"could not reach the rendezvous store at {host}:{port}: {last_err}")
+
+    def clone(self) -> "Rendezvous":
+        """A second client connection to the same store (for a helper thread)."""
+        c = Rendezvous.__new__(Rendezvous)
+        c.cluster, c.is_master, c.timeout_s = self.cluster, False, self.timeout_s
+        c._endpoint = self._endpoint
+        host, port = self._endpoint
+        c.store = TCPStore(host, port, world_size=None, is_master=False,
+                           timeout=datetime.timedelta(seconds=self.timeout_s), wait_for_workers=False)
+        return c
 
     def put(self, key: str, value) -> None:
         self.store.set(key, json.dumps(value))

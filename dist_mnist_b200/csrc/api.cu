@@ -12,6 +12,7 @@
 #include <string>
 
 #include "common.cuh"
+#include "fused.h"
 #include "protocol.h"
 
 namespace dm {
@@ -69,6 +70,10 @@ int dm_sizeof(const char* name) {
   if (!strcmp(name, "PsItemState")) return sizeof(PsItemState);
   if (!strcmp(name, "PsServeParams")) return sizeof(PsServeParams);
   if (!strcmp(name, "CUtensorMap")) return sizeof(CUtensorMap);
+  if (!strcmp(name, "FusedSlice")) return sizeof(FusedSlice);
+  if (!strcmp(name, "FusedShard")) return sizeof(FusedShard);
+  if (!strcmp(name, "FusedParams")) return sizeof(FusedParams);
+  if (!strcmp(name, "FusedMaps")) return sizeof(FusedMaps);
   return -1;
 }
 
@@ -83,6 +88,10 @@ int dm_device_count(int* n) {
 int dm_set_device(int dev) { DM_CUDA(cudaSetDevice(dev)); return 0; }
 int dm_device_sm_count(int dev, int* n) {
   DM_CUDA(cudaDeviceGetAttribute(n, cudaDevAttrMultiProcessorCount, dev));
+  return 0;
+}
+int dm_device_clock_khz(int dev, int* khz) {
+  DM_CUDA(cudaDeviceGetAttribute(khz, cudaDevAttrClockRate, dev));
   return 0;
 }
 int dm_device_cc(int dev, int* major, int* minor) {
@@ -142,6 +151,15 @@ int dm_stream_create(void** out) {
 }
 int dm_stream_destroy(void* s) { DM_CUDA(cudaStreamDestroy(static_cast<cudaStream_t>(s))); return 0; }
 int dm_stream_sync(void* s) { DM_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(s))); return 0; }
+// `waiter` does not run anything enqueued after this call until everything enqueued on `other` so far has finished
+int dm_stream_wait_stream(void* waiter, void* other) {
+  cudaEvent_t e;
+  DM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  DM_CUDA(cudaEventRecord(e, static_cast<cudaStream_t>(other)));
+  DM_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(waiter), e, 0));
+  DM_CUDA(cudaEventDestroy(e));
+  return 0;
+}
 int dm_stream_query(void* s) {  // 0 = idle, 1 = busy, <0 error
   cudaError_t e = cudaStreamQuery(static_cast<cudaStream_t>(s));
   if (e == cudaSuccess) return 0;
@@ -209,8 +227,25 @@ int dm_prepare_kernels(int dev) {
   DM_CUDA(dm::preload_head_kernels());
   DM_CUDA(dm::preload_ps_kernels());
   DM_CUDA(dm::preload_p2p_kernels());
+  DM_CUDA(dm::prepare_fused_kernel());
   return 0;
 }
+
+// Fused worker-step kernel (fused_step_sm100.cu): direct launch (tests / tools; the engine goes through fused_exec.cu)
+int dm_launch_fused(const void* maps, const void* params, int lanes, void* stream) {
+  dm::FusedMaps m;
+  dm::FusedParams p;
+  memcpy(&m, maps, sizeof(m));
+  memcpy(&p, params, sizeof(p));
+  DM_CUDA(dm::launch_fused_step(m, p, lanes, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int dm_fused_max_lanes(int dev, int* out) {
+  DM_CUDA(cudaSetDevice(dev));
+  DM_CUDA(dm::fused_max_lanes(out));
+  return 0;
+}
+int dm_fused_smem_bytes() { return static_cast<int>(dm::fused_smem_bytes()); }
 
 // head_params: HeadParams of the fused classifier head (GemmParams::fuse_head), or null
 int dm_launch_gemm_head(const void* tmA, const void* tmB, const void* params, const void* head_params, int dtype,

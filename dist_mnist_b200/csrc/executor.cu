@@ -27,9 +27,12 @@
 #include <thread>
 #include <vector>
 
+#include "loader.h"
 #include "protocol.h"
 
 namespace {
+
+using dm::BatchLoader;
 
 thread_local std::string g_exec_err;
 
@@ -42,47 +45,6 @@ int efail(const char* what, cudaError_t e) {
     cudaError_t e__ = (call);                          \
     if (e__ != cudaSuccess) return efail(#call, e__);  \
   } while (0)
-
-struct BatchLoader {
-  const uint8_t* images;
-  const uint8_t* labels;
-  size_t n;
-  size_t x_row_bytes, y_row_bytes;
-  size_t x_dst_stride, y_dst_stride;
-  int batch;
-  bool shuffle;
-  std::mt19937_64 rng;
-  std::vector<uint32_t> perm;
-  size_t cursor = 0;
-  uint64_t epochs = 0;
-
-  void reshuffle() {
-    if (shuffle) std::shuffle(perm.begin(), perm.end(), rng);
-  }
-  // next() = plan() + copy(): plan draws the batch's row indices (sequential: it owns the cursor, the epoch
-  // counter and the shuffle), copy moves the rows (the expensive part; safe to run on any thread).
-  void plan(uint32_t* idx_out) {
-    for (int r = 0; r < batch; ++r) {
-      if (cursor == n) {  // epoch boundary inside a batch: finish it from the next epoch (TF next_batch)
-        cursor = 0;
-        ++epochs;
-        reshuffle();
-      }
-      idx_out[r] = perm[cursor++];
-    }
-  }
-  void copy(const uint32_t* idx, uint8_t* x_dst, uint8_t* y_dst) const {
-    for (int r = 0; r < batch; ++r) {
-      memcpy(x_dst + r * x_dst_stride, images + static_cast<size_t>(idx[r]) * x_row_bytes, x_row_bytes);
-      memcpy(y_dst + r * y_dst_stride, labels + static_cast<size_t>(idx[r]) * y_row_bytes, y_row_bytes);
-    }
-  }
-  void next(uint8_t* x_dst, uint8_t* y_dst) {
-    std::vector<uint32_t> idx(batch);
-    plan(idx.data());
-    copy(idx.data(), x_dst, y_dst);
-  }
-};
 
 struct ExecSlot {
   void* x_dev = nullptr;          // into the group's device buffer

@@ -1,0 +1,508 @@
+// Native worker-side executor for the fused step kernel (fused_step_sm100.cu).
+//
+// The reference worker loop is `next_batch(32)` -> `sess.run(train_op, feed_dict)` -> read loss / global_step
+// (/root/reference/distributed_server-basic.py:110-116). Here the steps themselves run inside one persistent
+// kernel launch per *chunk* of steps; the executor's job is to keep that kernel fed:
+//
+//   gather pool  persistent helper threads run the `next_batch` loader (row gather into pinned staging memory;
+//                DRAM-latency bound, ~20 us per batch on one core) — created once, spinning only while a run is
+//                active, parked on a condition variable otherwise. No thread is spawned per call.
+//   chunks       a run of n steps is cut into chunks (4, 8, 16, 16, ... steps). Chunk c: gather -> one H2D copy of
+//                its x rows + one of its labels into a device ring buffer (copy stream) -> event -> one launch of
+//                the fused kernel for the chunk's steps (compute stream). Four chunk buffers rotate, so the gather
+//                and the transfer of chunk c+1 overlap the kernel of chunk c.
+//   results      every step's {loss, global_step, correct, seq} is written by the kernel straight into pinned host
+//                memory (posted PCIe write); a chunk's results are valid once its completion event has fired.
+//   resident     `run_resident`: one launch for any number of steps over a device-resident dataset (the kernel's TMA
+//                reads the batch rows directly out of the dataset; no staging copies at all).
+//
+// Everything is stream ordered — there is no kernel that waits for the host — so the path is safe under profilers
+// and sanitizers that serialise kernels.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "fused.h"
+#include "loader.h"
+
+namespace {
+
+thread_local std::string g_fx_err;
+
+int fxfail(const char* what, cudaError_t e) {
+  g_fx_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+  return -1;
+}
+#define FX_CUDA(call)                                   \
+  do {                                                  \
+    cudaError_t e__ = (call);                           \
+    if (e__ != cudaSuccess) return fxfail(#call, e__);  \
+  } while (0)
+
+inline void cpu_relax() {
+#if defined(__x86_64__)
+  __builtin_ia32_pause();
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// persistent gather pool
+// ---------------------------------------------------------------------------------------------
+struct GatherTask {
+  const dm::BatchLoader* loader;
+  std::vector<uint32_t> idx;   // batch row indices (planned by the submitting thread: the loader stays sequential)
+  uint8_t* x_dst;
+  uint8_t* y_dst;
+  std::atomic<uint32_t>* done;  // incremented when the batch is in place
+};
+
+struct GatherPool {
+  std::vector<std::thread> threads;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<GatherTask*> queue;
+  std::atomic<int> active{0};     // > 0 while some run is in progress: workers spin instead of sleeping
+  std::atomic<uint64_t> posted{0}, taken{0};
+  bool quit = false;
+
+  void start(int n) {
+    for (int t = 0; t < n; ++t) threads.emplace_back([this] { loop(); });
+  }
+  void stop() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      quit = true;
+    }
+    cv.notify_all();
+    for (auto& t : threads) t.join();
+    threads.clear();
+  }
+  GatherTask* try_pop() {
+    if (taken.load(std::memory_order_acquire) >= posted.load(std::memory_order_acquire)) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (queue.empty()) return nullptr;
+    GatherTask* t = queue.front();
+    queue.pop_front();
+    taken.fetch_add(1, std::memory_order_release);
+    return t;
+  }
+  void post(GatherTask* t) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      queue.push_back(t);
+      posted.fetch_add(1, std::memory_order_release);
+    }
+    cv.notify_one();
+  }
+  static void run_task(GatherTask* t) {
+    t->loader->copy(t->idx.data(), t->x_dst, t->y_dst);
+    std::atomic<uint32_t>* d = t->done;
+    delete t;
+    d->fetch_add(1, std::memory_order_release);
+  }
+  void loop() {
+    for (;;) {
+      GatherTask* t = try_pop();
+      if (t != nullptr) { run_task(t); continue; }
+      if (active.load(std::memory_order_acquire) > 0) { cpu_relax(); continue; }
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [this] { return quit || !queue.empty() || active.load(std::memory_order_acquire) > 0; });
+      if (quit && queue.empty()) return;
+    }
+  }
+};
+
+constexpr int kChunkMax = 16;   // steps per chunk buffer
+constexpr int kBuffers = 4;     // chunk buffers in rotation
+constexpr int kRowsPerSlot = 32;
+
+struct ChunkBuf {
+  cudaEvent_t copied = nullptr, done = nullptr;
+  std::atomic<uint32_t> gathered{0};
+  uint32_t n = 0;              // steps of the chunk currently occupying the buffer
+  bool in_flight = false;
+  uint64_t first_step = 0;     // index (within the run) of the chunk's first step
+};
+
+struct FusedExec {
+  int device = 0, lanes = 1, n_threads = 4;
+  int I = 0, C = 0, batch = 0;
+  size_t x_slot_bytes = 0, y_slot_bytes = 0;
+  uint8_t *x_dev = nullptr, *y_dev = nullptr, *x_stage = nullptr, *y_stage = nullptr;
+  dm::StepResult* res_chunks = nullptr;   // pinned [kBuffers][kChunkMax]
+  dm::StepResult* res_big = nullptr;      // pinned, grown on demand (run_resident / single steps)
+  size_t res_big_cap = 0;
+  uint32_t* ctl_dev = nullptr;            // [0] step counter, [1] stop word, [2] seq word (pushes made)
+  cudaStream_t compute = nullptr, copy = nullptr;
+  dm::FusedMaps maps{};
+  dm::FusedParams params{};
+  bool have_params = false;
+  uint64_t steps_done = 0;    // steps completed over the executor's lifetime == push sequence numbers used
+  uint64_t launches = 0;
+  ChunkBuf bufs[kBuffers];
+  GatherPool pool;
+  cudaEvent_t last_done = nullptr;  // completion of the most recent launch
+  uint64_t last_n = 0;              // steps requested by the most recent resident launch
+  dm::StepResult* last_results = nullptr;
+
+  int launch(const dm::FusedMaps& m, dm::FusedParams p, uint32_t n_steps, dm::StepResult* results, uint32_t stop_at,
+             bool reset_stop) {
+    p.n_steps = n_steps;
+    p.seq_base = static_cast<uint32_t>(steps_done);
+    p.stop_at = stop_at;
+    p.step_counter = ctl_dev;
+    p.stop_word = ctl_dev + 1;
+    p.seq_word = ctl_dev + 2;
+    p.results = results;
+    FX_CUDA(cudaMemsetAsync(ctl_dev, 0, reset_stop ? 8 : 4, compute));
+    FX_CUDA(dm::launch_fused_step(m, p, lanes, compute));
+    ++launches;
+    return 0;
+  }
+  int ensure_big(size_t n) {
+    if (n <= res_big_cap) return 0;
+    if (res_big) cudaFreeHost(res_big);
+    res_big = nullptr;
+    res_big_cap = 0;
+    size_t cap = 1024;
+    while (cap < n) cap <<= 1;
+    FX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&res_big), cap * sizeof(dm::StepResult),
+                          cudaHostAllocMapped | cudaHostAllocPortable));
+    res_big_cap = cap;
+    return 0;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* dm_fexec_last_error() { return g_fx_err.c_str(); }
+
+int dm_fexec_create(int device, int lanes, int I, int C, int batch, void** out) {
+  FX_CUDA(cudaSetDevice(device));
+  if (lanes < 1 || batch < 1 || batch > kRowsPerSlot || (I & 3) != 0) {
+    g_fx_err = "fused executor: need lanes >= 1, 1 <= batch <= 32, in_features % 4 == 0";
+    return -1;
+  }
+  FusedExec* ex = new FusedExec();
+  ex->device = device;
+  ex->lanes = lanes;
+  ex->I = I;
+  ex->C = C;
+  ex->batch = batch;
+  ex->x_slot_bytes = static_cast<size_t>(kRowsPerSlot) * I * 4;
+  ex->y_slot_bytes = static_cast<size_t>(kRowsPerSlot) * C * 4;
+  const size_t slots = static_cast<size_t>(kBuffers) * kChunkMax;
+  FX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ex->x_dev), slots * ex->x_slot_bytes));
+  FX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ex->y_dev), slots * ex->y_slot_bytes));
+  FX_CUDA(cudaMemset(ex->x_dev, 0, slots * ex->x_slot_bytes));
+  FX_CUDA(cudaMemset(ex->y_dev, 0, slots * ex->y_slot_bytes));
+  FX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ex->x_stage), slots * ex->x_slot_bytes, cudaHostAllocDefault));
+  FX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ex->y_stage), slots * ex->y_slot_bytes, cudaHostAllocDefault));
+  memset(ex->x_stage, 0, slots * ex->x_slot_bytes);
+  memset(ex->y_stage, 0, slots * ex->y_slot_bytes);
+  FX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ex->res_chunks), slots * sizeof(dm::StepResult),
+                        cudaHostAllocMapped | cudaHostAllocPortable));
+  memset(ex->res_chunks, 0, slots * sizeof(dm::StepResult));
+  FX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ex->ctl_dev), 64));
+  FX_CUDA(cudaMemset(ex->ctl_dev, 0, 64));
+  FX_CUDA(cudaStreamCreateWithFlags(&ex->compute, cudaStreamNonBlocking));
+  FX_CUDA(cudaStreamCreateWithFlags(&ex->copy, cudaStreamNonBlocking));
+  for (auto& b : ex->bufs) {
+    FX_CUDA(cudaEventCreateWithFlags(&b.copied, cudaEventDisableTiming));
+    FX_CUDA(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+  }
+  FX_CUDA(cudaEventCreateWithFlags(&ex->last_done, cudaEventDisableTiming));
+  if (ex->ensure_big(1u << 16) != 0) return -1;   // up front: no pinned allocation while a persistent ps kernel is resident
+  if (const char* e = getenv("DM_GATHER_THREADS")) ex->n_threads = std::max(1, atoi(e));
+  else ex->n_threads = static_cast<int>(std::min<unsigned>(8u, std::max(2u, std::thread::hardware_concurrency() / 2)));
+  ex->pool.start(ex->n_threads);
+  *out = ex;
+  return 0;
+}
+
+// Device / staging ring buffers: [kBuffers * kChunkMax slots][32 rows][I] fp32 and [..][32][C] fp32, and the control words.
+int dm_fexec_buffers(void* h, void** x_dev, void** y_dev, void** x_stage, void** y_stage, void** ctl_dev, int* slots) {
+  FusedExec* ex = static_cast<FusedExec*>(h);
+  *x_dev = ex->x_dev;
+  *y_dev = ex->y_dev;
+  *x_stage = ex->x_stage;
+  *y_stage = ex->y_stage;
+  *ctl_dev = ex->ctl_dev;
+  *slots = kBuffers * kChunkMax;
+  return 0;
+}
+
+// The launch template for steps fed through the ring: tensor maps over x_dev, y_base == y_dev, row geometry of the ring.
+int dm_fexec_set_params(void* h, const void* maps, const void* params) {
+  FusedExec* ex = static_cast<FusedExec*>(h);
+  memcpy(&ex->maps, maps, sizeof(dm::FusedMaps));
+  memcpy(&ex->params, params, sizeof(dm::FusedParams));
+  ex->have_params = true;
+  return 0;
+}
+
+void* dm_fexec_compute_stream(void* h) { return static_cast<FusedExec*>(h)->compute; }
+uint64_t dm_fexec_steps_done(void* h) { return static_cast<FusedExec*>(h)->steps_done; }
+uint64_t dm_fexec_launches(void* h) { return static_cast<FusedExec*>(h)->launches; }
+int dm_fexec_lanes(void* h) { return static_cast<FusedExec*>(h)->lanes; }
+// Clusters per launch from now on (steps of this worker in flight at once); the caller keeps it <= nslots.
+int dm_fexec_set_lanes(void* h, int lanes) {
+  if (lanes < 1) { g_fx_err = "set_lanes: lanes must be >= 1"; return -1; }
+  static_cast<FusedExec*>(h)->lanes = lanes;
+  return 0;
+}
+int dm_fexec_gather_threads(void* h) { return static_cast<FusedExec*>(h)->n_threads; }
+
+int dm_fexec_drain(void* h) {
+  FusedExec* ex = static_cast<FusedExec*>(h);
+  FX_CUDA(cudaStreamSynchronize(ex->copy));
+  FX_CUDA(cudaStreamSynchronize(ex->compute));
+  return 0;
+}
+
+// n steps (n <= kChunkMax) on host batches laid out like the staging ring (x [n][32][I], y [n][32][C]; rows >= batch
+// zero): H2D + one launch + wait. Results to out[n]. The `step()` / `submit` path of the public API.
+int dm_fexec_steps_host(void* h, const void* x_host, const void* y_host, uint32_t n, void* out, uint32_t* n_done) {
+  FusedExec* ex = static_cast<FusedExec*>(h);
+  if (!ex->have_params || n < 1 || n > kChunkMax) { g_fx_err = "steps_host: bad arguments"; return -1; }
+  FX_CUDA(cudaStreamSynchronize(ex->compute));   // buffer 0 must be free
+  memcpy(ex->x_stage, x_host, n * ex->x_slot_bytes);
+  memcpy(ex->y_stage, y_host, n * ex->y_slot_bytes);
+  memset(ex->res_chunks, 0, n * sizeof(dm::StepResult));
+  FX_CUDA(cudaMemcpyAsync(ex->x_dev, ex->x_stage, n * ex->x_slot_bytes, cudaMemcpyHostToDevice, ex->compute));
+  FX_CUDA(cudaMemcpyAsync(ex->y_dev, ex->y_stage, n * ex->y_slot_bytes, cudaMemcpyHostToDevice, ex->compute));
+  dm::FusedParams p = ex->params;
+  p.row_start = 0;
+  if (ex->launch(ex->maps, p, n, ex->res_chunks, 0, true) != 0) return -1;
+  FX_CUDA(cudaStreamSynchronize(ex->compute));
+  uint32_t done = 0;
+  dm::StepResult* o = static_cast<dm::StepResult*>(out);
+  for (uint32_t i = 0; i < n; ++i)
+    if (ex->res_chunks[i].seq != 0) o[done++] = ex->res_chunks[i];
+  ex->steps_done += done;
+  if (n_done) *n_done = done;
+  return 0;
+}
+
+// The native train loop: n_steps x { next_batch -> pinned staging -> H2D -> fused step -> result }, chunked and
+// pipelined as described in the file header. stop_at_global_step > 0: StopAtStepHook semantics (reference DS:101) —
+// no step is started once a finished step has reported global_step >= that value; *n_done = steps actually run.
+int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uint32_t stop_at_global_step,
+                 uint64_t* n_done) {
+  FusedExec* ex = static_cast<FusedExec*>(h);
+  dm::BatchLoader* ld = static_cast<dm::BatchLoader*>(loader);
+  dm::StepResult* out = static_cast<dm::StepResult*>(out_results);
+  if (!ex->have_params) { g_fx_err = "run: launch template not set"; return -1; }
+  if (ld->batch != ex->batch) { g_fx_err = "run: loader batch size differs from the executor's"; return -1; }
+  FX_CUDA(cudaSetDevice(ex->device));
+  FX_CUDA(cudaStreamSynchronize(ex->compute));
+  for (auto& b : ex->bufs) b.in_flight = false;
+  // chunk schedule: a short first chunk gets the GPU going while the bigger ones are being gathered
+  std::vector<uint32_t> sizes;
+  {
+    uint64_t left = n_steps;
+    uint32_t sz = 4;
+    while (left > 0) {
+      const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(left, sz));
+      sizes.push_back(n);
+      left -= n;
+      sz = std::min<uint32_t>(sz * 2, kChunkMax);
+    }
+  }
+  const size_t nchunks = sizes.size();
+  std::vector<uint64_t> first(nchunks + 1, 0);
+  for (size_t c = 0; c < nchunks; ++c) first[c + 1] = first[c] + sizes[c];
+  ex->pool.active.fetch_add(1, std::memory_order_release);
+  ex->pool.cv.notify_all();
+  uint64_t total_done = 0;
+  bool stop = false;
+  bool first_launch = true;
+  size_t next_gather = 0, next_launch = 0, next_harvest = 0;
+  int rc = 0;
+  auto harvest = [&](size_t c, bool wait) -> int {   // 1 = harvested, 0 = not ready, -1 = error
+    ChunkBuf& b = ex->bufs[c % kBuffers];
+    if (wait) {
+      if (cudaEventSynchronize(b.done) != cudaSuccess) return fxfail("cudaEventSynchronize", cudaGetLastError());
+    } else {
+      cudaError_t q = cudaEventQuery(b.done);
+      if (q == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+      if (q != cudaSuccess) return fxfail("cudaEventQuery", q);
+    }
+    const dm::StepResult* r = ex->res_chunks + (c % kBuffers) * kChunkMax;
+    for (uint32_t i = 0; i < b.n; ++i) {
+      if (r[i].seq == 0) continue;   // never claimed (stop)
+      if (out) out[total_done] = r[i];
+      ++total_done;
+      if (stop_at_global_step && r[i].global_step >= stop_at_global_step) stop = true;
+    }
+    b.in_flight = false;
+    return 1;
+  };
+  while (next_launch < nchunks && !stop) {
+    // ---- post gathers ahead (a buffer is free once the chunk that used it has been harvested) ----
+    while (next_gather < nchunks && next_gather < next_launch + kBuffers - 1) {
+      const size_t c = next_gather;
+      ChunkBuf& b = ex->bufs[c % kBuffers];
+      if (b.in_flight) {
+        while (next_harvest + kBuffers <= c) {   // the previous occupant must be complete before it is overwritten
+          const int hr = harvest(next_harvest, true);
+          if (hr < 0) { rc = -1; break; }
+          ++next_harvest;
+        }
+        if (rc != 0 || stop) break;
+      }
+      b.n = sizes[c];
+      b.first_step = first[c];
+      b.gathered.store(0, std::memory_order_relaxed);
+      b.in_flight = true;
+      const size_t slot0 = (c % kBuffers) * kChunkMax;
+      memset(ex->res_chunks + slot0, 0, sizes[c] * sizeof(dm::StepResult));
+      for (uint32_t i = 0; i < sizes[c]; ++i) {
+        GatherTask* t = new GatherTask();
+        t->loader = ld;
+        t->idx.resize(ld->batch);
+        ld->plan(t->idx.data());
+        t->x_dst = ex->x_stage + (slot0 + i) * ex->x_slot_bytes;
+        t->y_dst = ex->y_stage + (slot0 + i) * ex->y_slot_bytes;
+        t->done = &b.gathered;
+        ex->pool.post(t);
+      }
+      ++next_gather;
+    }
+    if (rc != 0 || stop) break;
+    // ---- launch the next chunk as soon as its batches are in place (this thread helps gathering meanwhile) ----
+    {
+      const size_t c = next_launch;
+      ChunkBuf& b = ex->bufs[c % kBuffers];
+      while (b.gathered.load(std::memory_order_acquire) < b.n) {
+        GatherTask* t = ex->pool.try_pop();
+        if (t != nullptr) GatherPool::run_task(t);
+        else cpu_relax();
+      }
+      const size_t slot0 = (c % kBuffers) * kChunkMax;
+      cudaError_t e;
+      e = cudaMemcpyAsync(ex->x_dev + slot0 * ex->x_slot_bytes, ex->x_stage + slot0 * ex->x_slot_bytes,
+                          b.n * ex->x_slot_bytes, cudaMemcpyHostToDevice, ex->copy);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(ex->y_dev + slot0 * ex->y_slot_bytes, ex->y_stage + slot0 * ex->y_slot_bytes,
+                            b.n * ex->y_slot_bytes, cudaMemcpyHostToDevice, ex->copy);
+      if (e == cudaSuccess) e = cudaEventRecord(b.copied, ex->copy);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(ex->compute, b.copied, 0);
+      if (e != cudaSuccess) { rc = fxfail("chunk transfer", e); break; }
+      dm::FusedParams p = ex->params;
+      p.row_start = static_cast<uint64_t>(slot0) * kRowsPerSlot;
+      // seq_base of this chunk assumes every earlier chunk of the run completes all its steps; if one is cut short
+      // by the stop condition the (persistent) stop word keeps every later chunk from claiming anything
+      const uint64_t saved = ex->steps_done;
+      ex->steps_done = saved + first[c];
+      const int lrc = ex->launch(ex->maps, p, b.n, ex->res_chunks + slot0, stop_at_global_step, first_launch);
+      ex->steps_done = saved;
+      if (lrc != 0) { rc = -1; break; }
+      first_launch = false;
+      e = cudaEventRecord(b.done, ex->compute);
+      if (e != cudaSuccess) { rc = fxfail("cudaEventRecord", e); break; }
+      ++next_launch;
+    }
+    // ---- non-blocking harvest (keeps the stop condition timely) ----
+    while (next_harvest < next_launch) {
+      const int hr = harvest(next_harvest, false);
+      if (hr < 0) { rc = -1; break; }
+      if (hr == 0) break;
+      ++next_harvest;
+    }
+    if (rc != 0) break;
+  }
+  // drain: batches gathered ahead of an early stop are dropped (their chunks were never launched)
+  while (rc == 0 && next_harvest < next_launch) {
+    if (harvest(next_harvest, true) < 0) { rc = -1; break; }
+    ++next_harvest;
+  }
+  for (size_t c = next_launch; c < next_gather; ++c) {   // wait for outstanding gather tasks of unlaunched chunks
+    ChunkBuf& b = ex->bufs[c % kBuffers];
+    while (b.gathered.load(std::memory_order_acquire) < b.n) {
+      GatherTask* t = ex->pool.try_pop();
+      if (t != nullptr) GatherPool::run_task(t);
+      else cpu_relax();
+    }
+    b.in_flight = false;
+  }
+  ex->pool.active.fetch_sub(1, std::memory_order_release);
+  if (rc != 0) return rc;
+  FX_CUDA(cudaStreamSynchronize(ex->compute));
+  ex->steps_done += total_done;
+  if (n_done) *n_done = total_done;
+  return 0;
+}
+
+// One launch for n_steps over a device-resident dataset: `maps` are tensor maps over the dataset, the batch of step s
+// is rows [(row_start + s * row_stride) % row_wrap, +32). Asynchronous: returns after enqueueing (dm_fexec_drain /
+// dm_fexec_resident_results complete it).
+int dm_fexec_run_resident(void* h, const void* maps, const void* y_base, uint64_t row_start, uint64_t row_stride,
+                          uint64_t row_wrap, uint64_t n_steps) {
+  FusedExec* ex = static_cast<FusedExec*>(h);
+  if (!ex->have_params || n_steps == 0 || n_steps > 0xFFFFFFF0ull) { g_fx_err = "run_resident: bad arguments"; return -1; }
+  if (ex->last_results == ex->res_big && ex->last_n != 0) FX_CUDA(cudaEventSynchronize(ex->last_done));
+  if (ex->ensure_big(n_steps) != 0) return -1;
+  memset(ex->res_big, 0, n_steps * sizeof(dm::StepResult));
+  dm::FusedMaps m;
+  memcpy(&m, maps, sizeof(m));
+  dm::FusedParams p = ex->params;
+  p.y_base = static_cast<const float*>(y_base);
+  p.row_start = row_start;
+  p.row_stride = row_stride;
+  p.row_wrap = row_wrap;
+  if (ex->launch(m, p, static_cast<uint32_t>(n_steps), ex->res_big, 0, true) != 0) return -1;
+  FX_CUDA(cudaEventRecord(ex->last_done, ex->compute));
+  ex->steps_done += n_steps;   // no stop condition on this path: every step runs
+  ex->last_n = n_steps;
+  ex->last_results = ex->res_big;
+  return 0;
+}
+
+// Wait for the most recent resident launch and copy its results (out may be null: just wait).
+int dm_fexec_resident_results(void* h, void* out, uint64_t max_n, uint64_t* n) {
+  FusedExec* ex = static_cast<FusedExec*>(h);
+  if (ex->last_n == 0) { if (n) *n = 0; return 0; }
+  FX_CUDA(cudaEventSynchronize(ex->last_done));
+  const uint64_t k = std::min<uint64_t>(ex->last_n, max_n);
+  if (out) memcpy(out, ex->last_results, k * sizeof(dm::StepResult));
+  if (n) *n = k;
+  return 0;
+}
+
+int dm_fexec_destroy(void* h) {
+  FusedExec* ex = static_cast<FusedExec*>(h);
+  cudaSetDevice(ex->device);
+  ex->pool.stop();
+  cudaStreamSynchronize(ex->copy);
+  cudaStreamSynchronize(ex->compute);
+  for (auto& b : ex->bufs) {
+    cudaEventDestroy(b.copied);
+    cudaEventDestroy(b.done);
+  }
+  cudaEventDestroy(ex->last_done);
+  cudaFree(ex->x_dev);
+  cudaFree(ex->y_dev);
+  cudaFree(ex->ctl_dev);
+  cudaFreeHost(ex->x_stage);
+  cudaFreeHost(ex->y_stage);
+  cudaFreeHost(ex->res_chunks);
+  if (ex->res_big) cudaFreeHost(ex->res_big);
+  cudaStreamDestroy(ex->compute);
+  cudaStreamDestroy(ex->copy);
+  delete ex;
+  return 0;
+}
+
+}  // extern "C"

@@ -105,7 +105,7 @@ void serve_loop(CpuPs* ps) {
         const uint32_t seq = P.next_seq[static_cast<size_t>(w) * P.n_items + item];
         const uint32_t slot = seq % P.nslots;
         seqs[w] = seq;
-        if (load_acquire(P.flags + (static_cast<size_t>(w) * P.nslots + slot) * P.n_items + item) == seq)
+        if (load_acquire(P.flags + (static_cast<size_t>(w) * P.nslots + slot) * P.n_flags + P.items[item].flag_index) == seq)
           mask |= 1u << w;
       }
       if (!mask) continue;

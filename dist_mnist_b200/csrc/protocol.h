@@ -137,6 +137,8 @@ struct PsItem {
   int rows, cols;
   int ld;
   int flags;        // bit0: refresh bf16 shadow for this block
+  int flag_index;   // which of the worker's per-push flags announces this block (several items may share one
+  int pad_;         //   flag: a pushed tile is applied by several ps CTAs, one sub-block each)
 };
 
 struct PsItemState {  // persisted across serve-kernel launches and checkpointed
@@ -160,6 +162,7 @@ struct PsServeParams {
   const PsItem* items;
   PsItemState* item_state;
   int n_items;
+  int n_flags;                 // flags per (worker, slot); PsItem::flag_index < n_flags
   int n_workers;
   int nslots;
   int opt;
@@ -167,7 +170,7 @@ struct PsServeParams {
   float lr, beta1, beta2, eps;
   const float* mailbox;        // [n_workers][nslots][arena_elems]
   uint64_t arena_elems;
-  uint32_t* flags;             // [n_workers][nslots][n_items]
+  uint32_t* flags;             // [n_workers][nslots][n_flags]
   uint32_t* next_seq;          // [n_workers][n_items] next expected push seq (persisted)
   uint32_t* consumed;          // [n_workers][nslots] items consumed of the in-flight push
   uint32_t* global_step;       // shard-local step counter (only shard 0's is authoritative)
@@ -179,10 +182,66 @@ struct PsServeParams {
   uint32_t* exit_counter;      // CTAs increment on exit (debug / clean shutdown)
   uint32_t gpu_scope;          // 1: every worker runs on the PS's own GPU (flags / acks at gpu scope)
   uint32_t lookahead;          // max pushes of one worker consumed per item pass (0 = auto: up to nslots)
+  uint32_t oneshot;            // 1: apply whatever is pending and exit after the first full sweep that finds nothing
+  uint32_t pad2_;              //    (stream-ordered after the workers' kernels: profiler / sanitizer safe)
   // Optional per-CTA serve statistics [gridDim.x][8] (accumulated over launches, written when a CTA exits):
   // passes with work, pushes applied, cycles in apply, cycles in bookkeeping, idle poll rounds, cycles idle,
   // largest number of pushes taken in one pass, poll cycles of working passes. Null = off.
   unsigned long long* stats;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Fused worker step (fused_step_sm100.cu): one 8-CTA thread-block cluster runs whole training steps of the
+// 784-H-10 MLP (H <= 128, batch <= 32) back to back inside one launch: TMA pull of its K-slice of W from the ps
+// shard, tcgen05 forward (split-K over the cluster, DSMEM reduce-scatter), classifier head, DSMEM all-gather of
+// the pre-activation gradient, tcgen05 dW of its own column slice, gradient push + flag. `lanes` clusters of one
+// launch work on different steps concurrently.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFusedCluster = 8;
+constexpr int kFusedMaxChunks = 4;   // 32-feature k-chunks per CTA  (in_features <= 8 * 4 * 32)
+constexpr int kFusedMaxShards = 8;
+constexpr uint32_t kFusedNoStep = 0xFFFFFFFFu;
+
+struct FusedSlice {        // what CTA `rank` of every cluster owns
+  int kc_begin;            // first k-chunk (x 32 input features)
+  int kc_count;            // 0 .. kFusedMaxChunks
+  int shard;               // index into FusedParams::shard of the ps shard that owns this column slice of W
+  int flag_index;          // flag (on that shard) announcing this CTA's dW tile
+  uint64_t w_offset;       // element offset of the hidden weight inside that shard's arena
+};
+
+struct FusedShard {        // one ps shard this worker pushes to
+  PushTarget push;         // mailbox / flags / mode of this worker on that shard (seq_ptr unused)
+  const uint32_t* inbox;   // local {ack_seq, global_step} pair the shard writes; null in atomic mode
+};
+
+struct FusedParams {
+  int B, H, C, I;          // batch (<= 32), hidden units (<= 128), classes (<= 11), input features
+  int loss_kind;
+  int ldw;                 // leading dimension of the hidden weight in the arena
+  int n_shards;
+  int strict;              // 1: pull W for a step only after every shard acknowledged this lane's previous push
+  FusedSlice slice[kFusedCluster];
+  FusedShard shard[kFusedMaxShards];
+  // small variables: where they live (peer pointers into the owning shard's params) and where their grads go
+  const float* bias_h; const float* w_last; const float* b_last;
+  int shard_bh, shard_wl, shard_bl;          // FusedParams::shard index owning hid_b / sm_w / sm_b
+  int flag_bh, flag_wl, flag_bl;             // their flag indices on those shards
+  uint64_t off_bh, off_wl, off_bl;           // element offsets inside those shards' arenas
+  // inputs: batch of step s = rows [(row_start + s * row_stride) % row_wrap, +32) of the x / y matrices
+  const float* y_base;
+  uint64_t row_start, row_stride, row_wrap;
+  // bookkeeping
+  uint32_t n_steps;        // steps of this launch (claimed dynamically by the clusters)
+  uint32_t seq_base;       // push sequence number of step s is seq_base + s + 1
+  uint32_t nslots;
+  uint32_t stop_at;        // > 0: no further steps are claimed once a step reports global_step >= stop_at
+  uint32_t* step_counter;  // device word, zeroed before the launch
+  uint32_t* stop_word;     // device word, zeroed before the launch
+  uint32_t* seq_word;      // device word: total pushes made by this worker (advanced at the end of every step)
+  uint32_t* ps_global_step;  // atomic mode: peer pointer to the shared step counter
+  StepResult* results;     // [n_steps] pinned host memory, written by the kernel
+  long long* debug_ts;     // optional phase stamps of cluster 0 / CTA 0
 };
 
 }  // namespace dm

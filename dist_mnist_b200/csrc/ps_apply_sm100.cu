@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
   const bool stats_on = P.stats != nullptr;
 
   for (;;) {
+    bool sweep_any = false;   // (uniform over the CTA: s_any is read after a barrier)
     for (int own = 0; own < n_own; ++own) {
       const int item = blockIdx.x + own * gridDim.x;
       const long long c0 = stats_on ? clock64() : 0;
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
           p_seq = s_next[own][pw] + pk;
           slot = p_seq % P.nslots;
           const uint32_t f = ld_acquire_scoped_u32(
-              P.flags + (static_cast<size_t>(pw) * P.nslots + slot) * P.n_items + item, P.gpu_scope);
+              P.flags + (static_cast<size_t>(pw) * P.nslots + slot) * P.n_flags + s_item[own].flag_index, P.gpu_scope);
           ready = (f == p_seq) ? 1u : 0u;
         }
         const uint32_t b = __ballot_sync(0xffffffffu, ready);
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
       const long long c1 = stats_on ? clock64() : 0;
       if (!s_any && stats_on) { ++st_idle_n; st_idle += c1 - c0; }
       if (s_any) {
+        sweep_any = true;
         const PsItemState st = s_state[own];
         apply_item(P, s_item[own], st, s_pend, s_round, static_cast<int>(s_npend));
         __syncthreads();   // every thread's parameter stores precede warp 0's release operations below
@@ -302,7 +304,10 @@ __global__ void __launch_bounds__(kPsThreads, 1) ps_serve_kernel(const __grid_co
     //  loop's period is the PS's reaction latency)
     if (tid == 0) {
       uint32_t ex = 0;
-      const bool check = (iter & 31u) == 0u;
+      // one-shot mode: everything that will ever be pushed was pushed before this launch (stream order), so a
+      // full sweep without work means the shard is up to date
+      if (P.oneshot && !sweep_any) ex = 1;
+      const bool check = !P.oneshot && (iter & 31u) == 0u;
       if (check && *P.host_stop != 0u) ex = 1;
       if (check && !ex) {
         bool all_done = true;

@@ -41,7 +41,18 @@ class EngineConfig:
     nslots: int = 2                  # mailbox slots per worker (pushes in flight before the worker waits for an ack)
     apply_mode: str = "per_push"     # "per_push" (reference semantics) | "merged"
     push_mode: str = "mailbox"       # "mailbox" (PS kernel applies; Adam or SGD) | "atomic" (SGD red.add, no PS kernel)
-    sharding: str = "round_robin"    # "round_robin" (reference parity) | "byte_balanced"
+    sharding: str = "round_robin"    # "round_robin" (reference parity) | "byte_balanced" | "row_split" (the hidden
+                                     # weight is split along its input features over every ps task; fused engine)
+    engine: str = "auto"             # "fused": one persistent kernel runs whole steps (784-H-10 models, H <= 128,
+                                     # batch <= 32, fp32) | "graph": per-layer kernels chained in a CUDA graph (any
+                                     # model / dtype) | "auto": fused when the model is eligible
+    strict_steps: bool = False       # fused engine: a lane pulls the weights of its next step only after the ps has
+                                     # acknowledged its previous push (the reference's read-your-writes order inside
+                                     # one worker); default: the pull overlaps the previous step's backward half
+    ps_row_blocks: int = 4           # fused tiling: ps items (CTAs) per pushed column slice of the hidden weight
+    ps_mode: str = "persistent"      # "persistent": resident serve kernel | "oneshot": the serve kernel is launched
+                                     # after the workers' kernels, applies what is pending and exits (in-process
+                                     # clusters under profilers / sanitizers; `smoke()`)
     ps_ctas: int = 0                 # CTAs of the persistent PS kernel (0 = auto: 120 on a dedicated ps GPU,
                                      # 32 when a worker shares the GPU)
     pipeline_slots: int = 4          # worker executor ring depth
@@ -76,6 +87,14 @@ class EngineConfig:
             raise ValueError(f"unknown backend {self.backend!r}")
         if self.push_mode not in ("mailbox", "atomic"):
             raise ValueError(f"unknown push_mode {self.push_mode!r}")
+        if self.engine not in ("auto", "fused", "graph"):
+            raise ValueError(f"unknown engine {self.engine!r} (auto | fused | graph)")
+        if self.ps_mode not in ("persistent", "oneshot"):
+            raise ValueError(f"unknown ps_mode {self.ps_mode!r} (persistent | oneshot)")
+        if self.sharding not in ("round_robin", "byte_balanced", "row_split"):
+            raise ValueError(f"unknown sharding {self.sharding!r}")
+        if self.ps_row_blocks < 1 or self.ps_row_blocks > 16:
+            raise ValueError("ps_row_blocks must be in [1, 16]")
         if self.push_mode == "atomic":
             if opt.kind != "sgd":
                 raise ValueError("push_mode='atomic' fuses the push with an SGD apply (red.add); use --optimizer sgd")
@@ -98,3 +117,18 @@ class EngineConfig:
 
     def as_dict(self) -> dict:
         return asdict(self)
+
+    def resolve_engine(self, spec, batch_size: int) -> str:
+        """Which step engine (and therefore which shard tiling) ps and worker tasks use. Both sides evaluate the
+        same rule from the same flags; the rendezvous descriptor check catches a mismatch."""
+        from .sharding import fused_eligible
+
+        ok = fused_eligible(spec, batch_size, self.dtype)
+        if self.engine == "fused" and not ok:
+            raise ValueError("engine 'fused' needs one hidden layer of <= 128 units, <= 11 classes, batch <= 32, fp32 "
+                             "and 8 <= ceil(in_features / 32) <= 32")
+        if self.engine == "graph" or not ok:
+            if self.sharding == "row_split":
+                raise ValueError("sharding 'row_split' needs the fused engine")
+            return "graph"
+        return "fused"

@@ -38,13 +38,14 @@ def shard_carver(shard: ShardLayout, n_workers: int, nslots: int) -> Carver:
     """Byte layout of one PS shard segment (both sides derive pointers from the exported table)."""
     a = shard.arena_elems
     ni = max(shard.n_items, 1)
+    nf = max(shard.n_flags, 1)
     c = Carver()
     c.add("params", a * 4)
     c.add("adam_m", a * 4)
     c.add("adam_v", a * 4)
     c.add("shadow", a * 2)
     c.add("mailbox", n_workers * nslots * a * 4)
-    c.add("flags", n_workers * nslots * ni * 4)
+    c.add("flags", n_workers * nslots * nf * 4)
     c.add("next_seq", n_workers * ni * 4)
     c.add("consumed", n_workers * nslots * 4)
     c.add("items", ni * C.sizeof(N.PsItem))
@@ -58,20 +59,23 @@ def shard_carver(shard: ShardLayout, n_workers: int, nslots: int) -> Carver:
 class ParameterServer:
     def __init__(self, cluster: ClusterSpec, task_index: int, spec: MLPSpec, opt: OptimizerConfig,
                  cfg: EngineConfig, device: int = 0, rdv: Optional[Rendezvous] = None,
-                 layout: Optional[ModelLayout] = None, verbose: bool = False):
+                 layout: Optional[ModelLayout] = None, verbose: bool = False, batch_size: int = 32):
         cfg.validate(opt)
         if cluster.num_workers > N.MAX_WORKERS:
             raise ValueError(f"at most {N.MAX_WORKERS} workers per ps shard")
         self.cluster, self.task_index, self.spec, self.opt, self.cfg = cluster, task_index, spec, opt, cfg
         self.device = device if cfg.backend == "cuda" else -1
         self.verbose = verbose
-        self.layout = layout or build_layout(spec, cluster.num_ps, cfg.sharding, dw_tile_n_for(cfg.dtype))
+        # the shard tiling follows the step engine the workers will use (same rule, same flags on both sides)
+        self.engine = layout.engine if layout is not None else cfg.resolve_engine(spec, batch_size)
+        self.layout = layout or build_layout(spec, cluster.num_ps, cfg.sharding, dw_tile_n_for(cfg.dtype),
+                                             engine=self.engine, ps_row_blocks=cfg.ps_row_blocks)
         self.shard = self.layout.shards[task_index]
         self.rdv = rdv or Rendezvous(cluster, "ps", task_index)
         self.n_workers = cluster.num_workers
         self.lib = N.lib()
         self._attached: Dict[int, Segment] = {}
-        self._attached_devices: List[int] = []
+        self._attached_device: Dict[int, int] = {}   # worker -> CUDA device of its current incarnation
         self._serving = False
         self._cpu_handle = None
         self._stream = None
@@ -80,6 +84,7 @@ class ParameterServer:
         self._cpu_table = (C.c_void_p * N.MAX_WORKERS)() if cfg.backend == "cpu" else None
         self._lock = threading.Lock()
         self._dead = set()          # workers declared dead by the failure detector
+        self._attached_at: Dict[int, float] = {}   # worker -> time its current incarnation was attached
         self._incarnation: Dict[int, int] = {}   # worker -> incarnation number currently attached
         self._readmit_restart = False
 
@@ -91,7 +96,8 @@ class ParameterServer:
         self._init_tables()
         desc = self.seg.export()
         desc.update({
-            "arena_elems": self.shard.arena_elems, "n_items": self.shard.n_items, "nslots": cfg.nslots,
+            "arena_elems": self.shard.arena_elems, "n_items": self.shard.n_items, "n_flags": self.shard.n_flags,
+            "nslots": cfg.nslots, "engine": self.engine,
             "n_workers": self.n_workers, "owns_global_step": self.shard.owns_global_step,
         })
         self.rdv.put(f"ps/{task_index}/segment", desc)
@@ -113,6 +119,7 @@ class ParameterServer:
         for i, it in enumerate(sh.items):
             items[i].offset, items[i].rows, items[i].cols, items[i].ld = it.offset, it.rows, it.cols, it.ld
             items[i].flags = 1 if (it.shadow and self.cfg.dtype == "bf16") else 0
+            items[i].flag_index = it.flag if it.flag >= 0 else i
         self._host_write("items", bytes(items))
         self.reset_optimizer_state()
         ones = (C.c_uint32 * (self.n_workers * ni))(*([1] * (self.n_workers * ni)))
@@ -133,6 +140,8 @@ class ParameterServer:
         P.shadow_bf16 = s.addr("shadow") if cfg.dtype == "bf16" else None
         P.items, P.item_state = s.addr("items"), s.addr("item_state")
         P.n_items, P.n_workers, P.nslots = sh.n_items, self.n_workers, cfg.nslots
+        P.n_flags = max(sh.n_flags, 1)
+        P.oneshot = 0
         P.opt, P.apply_mode = opt.native_kind, cfg.native_apply_mode
         P.lr, P.beta1, P.beta2, P.eps = opt.lr, opt.beta1, opt.beta2, opt.eps
         P.mailbox, P.arena_elems = s.addr("mailbox"), sh.arena_elems
@@ -144,8 +153,8 @@ class ParameterServer:
         # flags / acks need system scope only when some worker sits on another GPU
         P.lookahead = int(os.environ.get("DM_PS_LOOKAHEAD", "0"))
         P.stats = s.addr("stats") if (cfg.backend == "cuda" and os.environ.get("DM_PS_STATS") == "1") else None
-        P.gpu_scope = int(cfg.backend == "cuda" and self.n_workers == 1 and len(self._attached_devices) == 1
-                          and self._attached_devices[0] == self.device)
+        devs = list(self._attached_device.values())
+        P.gpu_scope = int(cfg.backend == "cuda" and self.n_workers == 1 and len(devs) == 1 and devs[0] == self.device)
         if cfg.backend == "cuda":
             P.inbox_table = s.addr("inbox_table")
         else:
@@ -168,6 +177,7 @@ class ParameterServer:
             return
         P = self._serve_params()
         self._P = P
+        self.oneshot = self.cfg.ps_mode == "oneshot" and self.cfg.backend == "cuda"
         if self.cfg.backend == "cuda":
             N.check(self.lib.dm_set_device(self.device), "set device")
             N.ensure_prepared(self.device)  # load every kernel before the persistent one becomes resident
@@ -178,12 +188,29 @@ class ParameterServer:
             self._ctl_stream = out.value
             N.check(self.lib.dm_host_alloc(4096, C.byref(out)))
             self._pin = out.value
-            n_ctas = self._serve_ctas()
-            N.check(self.lib.dm_launch_ps_serve(C.addressof(P), n_ctas, self._stream), "launch ps_serve")
+            if self.oneshot:
+                P.oneshot = 1   # nothing resident: `serve_once()` runs the kernel after the workers' kernels
+            else:
+                n_ctas = self._serve_ctas()
+                N.check(self.lib.dm_launch_ps_serve(C.addressof(P), n_ctas, self._stream), "launch ps_serve")
         else:
             self._cpu_handle = self.lib.dm_cpu_ps_start(C.addressof(P))
         self._serving = True
-        self.rdv.put(f"ps/{self.task_index}/serving", {"mode": "mailbox"})
+        self.rdv.put(f"ps/{self.task_index}/serving", {"mode": "oneshot" if self.oneshot else "mailbox"})
+
+    def serve_once(self, after_stream: Optional[int] = None, wait: bool = True) -> None:
+        """One-shot mode: launch the serve kernel once; it applies every push that is complete in memory and exits
+        after the first sweep that finds nothing (csrc/ps_apply_sm100.cu, PsServeParams::oneshot). `after_stream`:
+        a CUDA stream whose enqueued work (the worker's step kernels) must finish first — the launch is ordered
+        behind it with an event, so nothing ever waits for a kernel that has not been launched: safe under
+        profilers and sanitizers that serialise kernels."""
+        if not getattr(self, "oneshot", False) or not self._serving:
+            return
+        if after_stream is not None:
+            N.check(self.lib.dm_stream_wait_stream(self._stream, after_stream), "order serve after worker")
+        N.check(self.lib.dm_launch_ps_serve(C.addressof(self._P), self._serve_ctas(), self._stream), "launch ps_serve")
+        if wait:
+            N.check(self.lib.dm_stream_sync(self._stream), "one-shot ps serve kernel")
 
     # ------------------------------------------------------------------------------------------
     def _patch_table(self, w: int, ptr: int) -> None:
@@ -216,7 +243,8 @@ class ParameterServer:
                 seg = Segment.open(desc, device=self.device)
                 self._attached[w] = seg
                 self._incarnation[w] = desc.get("incarnation", 1)
-                self._attached_devices.append(desc.get("worker_device", -1))
+                self._attached_device[w] = desc.get("worker_device", -1)
+                self._attached_at[w] = time.time()
                 ptr = seg.addr("inbox", 8 * desc["inbox_index"][str(self.task_index)]) \
                     if str(self.task_index) in desc["inbox_index"] else 0
                 if ptr:
@@ -236,30 +264,37 @@ class ParameterServer:
         print(f"[ps {self.task_index}] worker {w} re-registered (incarnation "
               f"{self.rdv.add(f'worker/{w}/incarnation', 0)}): re-admitting it", flush=True)
         old = self._attached.pop(w)
-        try:
-            old.close()
-        except Exception:
-            pass               # the process that exported it is gone
+        self._attached_device.pop(w, None)
         if self.cfg.push_mode == "atomic":
+            try:
+                old.close()
+            except Exception:
+                pass               # the process that exported it is gone
             if w in self._dead and self.task_index == 0:
                 self.rdv.add("session/workers_done", -1)
             self._dead.discard(w)
             return
-        was_serving = self._serving
+        # order matters: the serve loop / kernel may still acknowledge an old push into the previous incarnation's
+        # inbox, so it is stopped and the table entry cleared *before* that mapping goes away
+        was_serving = self._serving and not getattr(self, "oneshot", False)
         if was_serving:
             self.stop()
-        ni, ns = max(self.shard.n_items, 1), self.cfg.nslots
-        self._host_write("flags", bytes(4 * ns * ni), 4 * w * ns * ni)
+        self._patch_table(w, 0)
+        try:
+            old.close()
+        except Exception:
+            pass                   # the process that exported it is gone
+        ni, ns, nf = max(self.shard.n_items, 1), self.cfg.nslots, max(self.shard.n_flags, 1)
+        self._host_write("flags", bytes(4 * ns * nf), 4 * w * ns * nf)
         self._host_write("consumed", bytes(4 * ns), 4 * w * ns)
         self._host_write("next_seq", bytes((C.c_uint32 * ni)(*([1] * ni))), 4 * w * ni)
         self._host_write("ctrl", bytes(4), 4 * (CTRL_WORKER_DONE + w))
-        self._patch_table(w, 0)
         self._dead.discard(w)
         self._readmit_restart = was_serving
 
     # ------------------------------------------------------------------------------------------
     def kernel_running(self) -> bool:
-        if not self._serving or self.cfg.push_mode == "atomic":
+        if not self._serving or self.cfg.push_mode == "atomic" or getattr(self, "oneshot", False):
             return False
         if self.cfg.backend == "cuda":
             return self.lib.dm_stream_query(self._stream) == 1
@@ -278,7 +313,9 @@ class ParameterServer:
         """Ask the serve kernel / loop to exit and wait for it."""
         if not self._serving:
             return
-        if self.cfg.push_mode != "atomic":
+        if self.cfg.push_mode != "atomic" and getattr(self, "oneshot", False):
+            N.check(self.lib.dm_stream_sync(self._stream), "one-shot ps serve kernel")
+        elif self.cfg.push_mode != "atomic":
             if self.cfg.backend == "cuda":
                 C.c_uint32.from_address(self._pin + 1024).value = 1
                 N.check(self.lib.dm_memcpy_async(self.seg.addr("ctrl", 4 * CTRL_HOST_STOP), self._pin + 1024, 4,
@@ -303,7 +340,9 @@ class ParameterServer:
         if not rows:
             return None
         tot = [sum(r[j] for r in rows) for j in range(8)]
-        mhz = 1965.0
+        khz = C.c_int(0)
+        N.check(self.lib.dm_device_clock_khz(self.device, C.byref(khz)))
+        mhz = khz.value / 1e3   # the device's maximum SM clock: cycle counts -> lower-bound microseconds
         return {
             "ctas": len(rows), "passes": tot[0], "pushes": tot[1],
             "pushes_per_pass": round(tot[1] / max(tot[0], 1), 2), "max_pushes_in_pass": max(r[6] for r in rows),
@@ -319,8 +358,8 @@ class ParameterServer:
         shared with a worker keeps most SMs for the worker's step kernels."""
         want = self.cfg.ps_ctas
         if want <= 0:
-            shared = any(d == self.device for d in self._attached_devices)
-            want = 32 if shared else 120
+            shared = any(d == self.device for d in self._attached_device.values())
+            want = 40 if shared else 128
         return max(1, min(want, self.shard.n_items))
 
     def restart(self) -> None:
@@ -330,6 +369,9 @@ class ParameterServer:
         if self._serving:
             return
         if self.cfg.push_mode == "atomic":
+            self._serving = True
+            return
+        if getattr(self, "oneshot", False):
             self._serving = True
             return
         if self.cfg.backend == "cuda":
@@ -365,6 +407,27 @@ class ParameterServer:
             self.lib.dm_store_release_u32(addr, N.WORKER_DEAD)
         self._dead.add(w)
 
+    def revive_worker(self, w: int) -> None:
+        """Undo `mark_worker_dead` for a worker whose heartbeat resumed (it was slow, not dead): its inbox pointer is
+        restored and the serve loop waits for its pushes again. Pushes it completed meanwhile were applied anyway —
+        only the acknowledgements were suppressed."""
+        seg = self._attached.get(w)
+        if seg is None:
+            return
+        desc = self.rdv.try_get(f"worker/{w}/inbox") or {}
+        idx = desc.get("inbox_index", {}).get(str(self.task_index))
+        addr = self.seg.addr("ctrl", 4 * (CTRL_WORKER_DONE + w))
+        if self.cfg.backend == "cuda":
+            C.c_uint32.from_address(self._pin + 1032).value = 0
+            N.check(self.lib.dm_memcpy_async(addr, self._pin + 1032, 4, self._ctl_stream))
+            N.check(self.lib.dm_stream_sync(self._ctl_stream))
+        else:
+            self.lib.dm_store_release_u32(addr, 0)
+        if idx is not None:
+            self._patch_table(w, seg.addr("inbox", 8 * idx))
+        self._dead.discard(w)
+        print(f"[ps {self.task_index}] worker {w} is alive again (heartbeat resumed)", flush=True)
+
     def check_worker_liveness(self, timeout_s: float) -> List[int]:
         """Declare dead every attached worker that has neither finished nor sent a heartbeat for `timeout_s`
         seconds (workers heartbeat through the rendezvous store once per train-loop chunk). Returns the workers
@@ -372,10 +435,16 @@ class ParameterServer:
         newly = []
         now = time.time()
         for w in list(self._attached):
-            if w in self._dead:
-                continue
             hb = self.rdv.try_get(f"session/heartbeat/{w}")
-            if hb is None or now - float(hb) <= timeout_s:
+            if w in self._dead:
+                # a worker that was only slow (long graph capture, a paused process) heartbeats again: take it back
+                if hb is not None and now - float(hb) <= timeout_s and self.cfg.push_mode != "atomic":
+                    self.revive_worker(w)
+                continue
+            # the liveness clock starts when this incarnation was attached by *this* shard, not at its first heartbeat
+            # (a non-chief worker connects long before the chief has finished initialising)
+            last = max(float(hb) if hb is not None else 0.0, self._attached_at.get(w, now))
+            if hb is None or now - last <= timeout_s:
                 continue
             if self.cfg.push_mode != "atomic" and self._worker_done_word(w) != 0:
                 continue   # it left the session cleanly
@@ -408,8 +477,14 @@ class ParameterServer:
                 if self.cfg.push_mode == "atomic":
                     if self.rdv.add("session/workers_done", 0) >= self.n_workers:
                         break
+                elif getattr(self, "oneshot", False):
+                    if self.rdv.add("session/workers_done", 0) >= self.n_workers:
+                        self.serve_once()
+                        break
                 elif self._serving and not self.kernel_running():
                     break
+            if getattr(self, "oneshot", False):
+                self.serve_once()      # one-shot mode as a stand-alone task: apply whatever has arrived
             time.sleep(poll_s)
         self.stop()
 

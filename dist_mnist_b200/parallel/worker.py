@@ -7,12 +7,14 @@ Reference parity (`/root/reference/distributed_server-basic.py`):
   * DS:110-113  one step = pull variables, forward/backward on the worker, push gradients, PS applies Adam and
                 bumps `global_step`; the worker gets `loss` and `global_step` back. No locks, no barriers.
 
-GPU backend: a step is a PDL-linked chain of hand-written sm_100a kernels inside a CUDA graph (see `ops/`): the
-forward GEMMs pull their weight tiles straight out of the PS shard's HBM with TMA over NVLink, the dW GEMM
-epilogues and the classifier-head kernel push gradients into the PS mailbox (or red.add them into the master
-copy for SGD) and publish per-tile flags; the persistent PS kernel applies. The native executor keeps
-`cfg.lanes` steps in flight, launches `cfg.graph_steps` of them per graph, gathers batches on helper threads
-and receives each step's 16-byte result in pinned host memory (csrc/executor.cu).
+GPU backend, two step engines (`EngineConfig.engine`, resolved by `EngineConfig.resolve_engine`):
+  * "fused" (784-H-10 models, H <= 128, batch <= 32, fp32 — the reference's live configuration): whole steps run
+    inside one persistent kernel (csrc/fused_step_sm100.cu): an 8-CTA cluster pulls its K-slices of W from the ps
+    shard(s) with TMA over NVLink, tcgen05 forward with a DSMEM reduce-scatter, head, DSMEM all-gather, tcgen05 dW
+    whose epilogue pushes into the ps mailbox; `cfg.lanes` clusters work on different steps concurrently. The
+    native executor (csrc/fused_exec.cu) feeds it chunk by chunk: gather pool -> pinned staging -> H2D -> one launch.
+  * "graph" (any depth / width / bf16): a PDL-linked chain of per-layer kernels inside a CUDA graph (`ops/`,
+    csrc/gemm_sm100.cu, csrc/head_sm100.cu) driven by csrc/executor.cu.
 
 CPU backend: same protocol over POSIX shm with torch CPU math (BASELINE.json config 1, plumbing tests).
 """
@@ -20,6 +22,7 @@ from __future__ import annotations
 
 import collections.abc
 import ctypes as C
+import os
 import time
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -36,7 +39,7 @@ from ..ops import head as head_ops
 from .config import MAX_SLOTS, EngineConfig, OptimizerConfig
 from .peer_mem import Carver, Segment
 from .ps import CTRL_GLOBAL_STEP, CTRL_WORKER_DONE
-from .sharding import ModelLayout, VarLayout, build_layout, dw_tile_n_for
+from .sharding import FUSED_CLUSTER, ModelLayout, VarLayout, build_layout, dw_tile_n_for
 
 
 @dataclass
@@ -91,13 +94,19 @@ class Worker:
         self.B_pad = _round_up(batch_size, 16)
         self.device = device if cfg.backend == "cuda" else -1
         self.verbose = verbose
-        self.layout = layout or build_layout(spec, cluster.num_ps, cfg.sharding, dw_tile_n_for(cfg.dtype))
+        self.engine = layout.engine if layout is not None else cfg.resolve_engine(spec, batch_size)
+        self.layout = layout or build_layout(spec, cluster.num_ps, cfg.sharding, dw_tile_n_for(cfg.dtype),
+                                             engine=self.engine, ps_row_blocks=cfg.ps_row_blocks)
+        if self.engine == "fused":
+            self.B_pad = N.FUSED_ROWS_PER_SLOT   # the fused kernel always works on 32-row tiles (rows >= batch masked)
         self.rdv = rdv or Rendezvous(cluster, "worker", task_index)
         self.lib = N.lib()
         self.is_chief = task_index == 0  # DS:108
         self.ps_segs: List[Segment] = []
         self.seg: Optional[Segment] = None
         self._exec = None
+        self._fexec = None          # fused engine: native executor handle (csrc/fused_exec.cu)
+        self._ps_local: List = []   # in-process clusters with one-shot ps tasks: serve after every launch
         self._connected = False
         self._closed = False
         self._seq_host = 0          # cpu backend: push sequence number
@@ -108,7 +117,12 @@ class Worker:
         # shards this worker pushes to, the one owning global_step first (its inbox entry is index 0)
         used = [sh.ps for sh in self.layout.shards if sh.n_items > 0]
         gs_owner = self.layout.placement["global_step"]
-        self.gs_owner = gs_owner
+        # The shared step counter is the one of the first shard in `inbox_order` (its serve loop counts fully applied
+        # pushes and reports the count with every acknowledgement). Normally that is the shard placement gives
+        # `global_step` to; when that shard owns no variable at all (more ps tasks than variables) no serve loop ever
+        # increments its counter, so the counter of the first shard that does own items is authoritative instead.
+        self.gs_owner = gs_owner if (gs_owner in used or not used) else used[0]
+        gs_owner = self.gs_owner
         self.inbox_order = ([gs_owner] if gs_owner in used else []) + [k for k in used if k != gs_owner]
         self.inbox_index = {k: i for i, k in enumerate(self.inbox_order)}
         self.kernels_per_step = 0
@@ -127,8 +141,12 @@ class Worker:
             desc = self.rdv.get(f"ps/{k}/segment", timeout_s)
             if desc["nslots"] != cfg.nslots or desc["n_workers"] != self.cluster.num_workers:
                 raise RuntimeError(f"ps {k} was started with a different engine configuration: {desc}")
-            if desc["arena_elems"] != self.layout.shards[k].arena_elems or desc["n_items"] != self.layout.shards[k].n_items:
-                raise RuntimeError(f"ps {k} has a different model layout (model / sharding flags differ?)")
+            sh = self.layout.shards[k]
+            if (desc["arena_elems"] != sh.arena_elems or desc["n_items"] != sh.n_items
+                    or desc.get("n_flags", sh.n_flags) != sh.n_flags or desc.get("engine", self.engine) != self.engine):
+                raise RuntimeError(f"ps {k} has a different model layout (model / batch_size / sharding / engine "
+                                   f"flags differ?): ps {desc.get('engine')} {desc['n_items']} items, "
+                                   f"worker {self.engine} {sh.n_items} items")
             self.ps_desc.append(desc)
             self.ps_segs.append(Segment.open(desc, device=self.device))
         carver = Carver()
@@ -146,6 +164,7 @@ class Worker:
         desc["incarnation"] = self.incarnation
         self.rdv.put(f"worker/{self.task_index}/inbox", desc)
         self.heartbeat()
+        self._start_heartbeat_thread()
         self._connected = True
 
     def wait_ready(self, timeout_s: Optional[float] = None) -> None:
@@ -154,7 +173,9 @@ class Worker:
         for k in range(self.cluster.num_ps):
             self.rdv.get(f"ps/{k}/serving", timeout_s)
             self.rdv.get(f"ps/{k}/attached/{self.task_index}/{self.incarnation}", timeout_s)
+        self.heartbeat()
         self.prepare()
+        self.heartbeat()
         # seed our view of the shared step counter (a restored session does not start at 0)
         g0 = self.read_global_step()
         if self.cfg.backend == "cuda":
@@ -172,19 +193,37 @@ class Worker:
             return list(host)
         return [self.lib.dm_load_acquire_u32(self.seg.addr(region, byte_offset + 4 * i)) for i in range(count)]
 
+    def _seq_word_ptr(self) -> int:
+        """Device word holding the number of pushes this worker has made (read by wait_ack / worker_done kernels)."""
+        if self.engine == "fused" and self._fexec:
+            return self._fx_ctl + 8
+        return self.seg.addr("seq")
+
     def pushes_made(self) -> int:
         if self.cfg.backend == "cuda":
             self.drain()
+            if self.engine == "fused":
+                return int(self.lib.dm_fexec_steps_done(self._fexec)) if self._fexec else 0
             return self._read_own("seq", 1)[0]
         return self._seq_host
 
     def wait_applied(self, timeout_s: float = 60.0) -> None:
         """Block until every push this worker has made is applied on every shard (needed for a consistent
-        checkpoint or evaluation; training itself never waits like this)."""
-        if self.cfg.push_mode != "mailbox" or not self.inbox_order:
+        checkpoint or evaluation; training itself never waits like this). GPU: a one-thread kernel on the compute
+        stream spins on the locally written acknowledgement words, the host just synchronises the stream."""
+        if self.cfg.backend == "cuda":
+            self._serve_local()
             self.drain()
+            if self.cfg.push_mode != "mailbox" or not self.inbox_order or (self._exec is None and self._fexec is None):
+                return
+            stream = self.compute_stream
+            N.check(self.lib.dm_launch_wait_ack(self.seg.addr("inbox"), len(self.inbox_order), self._seq_word_ptr(),
+                                                stream), "wait_ack")
+            N.check(self.lib.dm_stream_sync(stream), "wait for the ps acknowledgements")
             return
-        seq = self.pushes_made()
+        if self.cfg.push_mode != "mailbox" or not self.inbox_order:
+            return
+        seq = self._seq_host
         t0 = time.time()
         while True:
             inbox = self._read_own("inbox", 2 * len(self.inbox_order))
@@ -192,18 +231,58 @@ class Worker:
                 return
             if time.time() - t0 > timeout_s:
                 raise TimeoutError(f"pushes up to {seq} not acknowledged: inbox={inbox}")
-            time.sleep(0.0005)
+            time.sleep(0.0002)
+
+    def attach_local_ps(self, ps_list) -> None:
+        """In-process clusters whose ps tasks run in one-shot mode: after every launch of step kernels the worker
+        lets those ps tasks run their serve kernel once (stream-ordered behind the steps)."""
+        self._ps_local = [p for p in ps_list if getattr(p, "oneshot", False)]
+
+    def _serve_local(self) -> None:
+        if self._ps_local and (self._exec or self._fexec):
+            stream = self.compute_stream
+            for p in self._ps_local:
+                p.serve_once(after_stream=stream, wait=True)
 
     def heartbeat(self) -> None:
         """Liveness mark for the ps-side failure detector (`ParameterServer.join(worker_timeout_s=...)`)."""
         self.rdv.put(f"session/heartbeat/{self.task_index}", time.time())
 
+    def _start_heartbeat_thread(self, period_s: float = 0.5) -> None:
+        """Process-level liveness: a daemon thread with its own store connection refreshes the heartbeat twice a
+        second for as long as this process lives (a crash, `os._exit` or `kill -9` silences it at once), so a worker
+        that is merely busy — graph capture, a long chunk of steps on a loaded box, waiting for the chief — is never
+        mistaken for a dead one, however small `--worker_timeout` is."""
+        if getattr(self, "_hb_thread", None) is not None:
+            return
+        import threading
+
+        self._hb_stop = threading.Event()
+        key = f"session/heartbeat/{self.task_index}"
+
+        def loop():
+            try:
+                rdv = self.rdv.clone()
+            except Exception:
+                return
+            while not self._hb_stop.wait(period_s):
+                try:
+                    rdv.put(key, time.time())
+                except Exception:
+                    return      # the store is gone: the session is over
+
+        self._hb_thread = threading.Thread(target=loop, name="dm-heartbeat", daemon=True)
+        self._hb_thread.start()
+
     def prepare(self) -> None:
         """Build the step graphs (GPU backend). Only needs the PS pointers, so it may run before the variables
         are initialised — in-process clusters call it before the persistent PS kernel is launched so that no
         allocation happens while that kernel owns part of the GPU."""
-        if self.cfg.backend == "cuda" and self._exec is None:
-            self._build_cuda()
+        if self.cfg.backend == "cuda" and self._exec is None and self._fexec is None:
+            if self.engine == "fused":
+                self._build_fused()
+            else:
+                self._build_cuda()
 
     # ------------------------------------------------------------------------------------------
     # variable I/O through peer memory (chief init / restore, checkpoints, evaluation)
@@ -250,15 +329,29 @@ class Worker:
             if tuple(t.shape) != tuple(vl.spec.shape):
                 raise ValueError(f"{name}: expected shape {vl.spec.shape}, got {tuple(t.shape)}")
             flat = self._pack(vl, t)
-            self._copy_to_ps(vl.ps, region, vl.offset, flat)
-            if region == "params" and self.cfg.dtype == "bf16":
-                self._copy_to_ps(vl.ps, "shadow", vl.offset, flat.to(torch.bfloat16))
+            # a column-split variable keeps its full span on every owning shard (each shard updates its own columns)
+            for k, off in dict.fromkeys((pc.ps, pc.offset) for pc in vl.pieces):
+                self._copy_to_ps(k, region, off, flat)
+                if region == "params" and self.cfg.dtype == "bf16":
+                    self._copy_to_ps(k, "shadow", off, flat.to(torch.bfloat16))
 
     def read_variables(self, region: str = "params") -> Dict[str, torch.Tensor]:
         out = {}
         for name, vl in self.layout.by_name.items():
-            flat = self._copy_from_ps(vl.ps, region, vl.offset, vl.span, torch.float32)
-            out[name] = self._unpack(vl, flat)
+            if len({(pc.ps, pc.offset) for pc in vl.pieces}) == 1:   # one owner (whole variable, or all slices there)
+                flat = self._copy_from_ps(vl.ps, region, vl.offset, vl.span, torch.float32)
+                out[name] = self._unpack(vl, flat)
+                continue
+            full = torch.empty(vl.rows, vl.cols)
+            cache: Dict[Tuple[int, int], torch.Tensor] = {}
+            for pc in vl.pieces:
+                if pc.c1 <= pc.c0:
+                    continue
+                if (pc.ps, pc.offset) not in cache:
+                    cache[(pc.ps, pc.offset)] = self._unpack(
+                        vl, self._copy_from_ps(pc.ps, region, pc.offset, vl.span, torch.float32))
+                full[:, pc.c0:pc.c1] = cache[(pc.ps, pc.offset)][:, pc.c0:pc.c1]
+            out[name] = full
         return out
 
     def read_global_step(self) -> int:
@@ -286,6 +379,12 @@ class Worker:
         self.write_variables(zeros, "adam_v")
         self.rdv.put("init/done", {"seed": seed, "by": self.task_index})
 
+    def variables_are_live(self) -> bool:
+        """True when some chief incarnation has already initialised (or restored) the variables on the ps tasks of
+        this session. A restarted chief must then *not* run the initialisers again: the shards keep training state
+        (parameters, Adam slots, per-item step counts, global_step) that the other workers are still updating."""
+        return self.rdv.try_get("init/done") is not None
+
     def mark_initialized(self) -> None:
         """Chief-only: announce that the variables on the PS are valid (after a checkpoint restore)."""
         self.rdv.put("init/done", {"restored": True, "by": self.task_index})
@@ -297,7 +396,7 @@ class Worker:
         seg, desc = self.ps_segs[k], self.ps_desc[k]
         t = N.PushTarget()
         w = self.task_index
-        arena, ni, ns = desc["arena_elems"], max(desc["n_items"], 1), self.cfg.nslots
+        arena, ni, ns = desc["arena_elems"], max(desc.get("n_flags", desc["n_items"]), 1), self.cfg.nslots
         if self.cfg.push_mode == "atomic":
             t.mode, t.scale, t.base = N.PUSH_ATOMIC, -self.opt.lr, seg.addr("params")
             t.nslots = 1
@@ -465,12 +564,109 @@ class Worker:
                     N.check(self.lib.dm_exec_end_group_capture(self._exec, g), "end group capture")
 
     # ------------------------------------------------------------------------------------------
+    # fused engine construction
+    # ------------------------------------------------------------------------------------------
+    def _fused_maps(self, x_ptr: int, n_rows: int) -> N.FusedMaps:
+        """Tensor maps of one fused launch: W K-slices on the owning shards (NVLink peer mappings) and the two views
+        of the x matrix [n_rows][in] the batches are taken from."""
+        lay, I = self.layout, self.spec.in_features
+        wname = self.spec.variable_names()[0][0]
+        vl = lay.by_name[wname]
+        m = N.FusedMaps()
+        for sl in lay.fused_slices:
+            seg = self.ps_segs[sl.ps]
+            tm = N.make_tensor_map(seg.addr("params", sl.w_offset * 4), N.DT_F32, I, vl.rows, vl.ld * 4, 32, 128)
+            C.memmove(C.addressof(m.w[sl.rank]), C.addressof(tm), N.TENSOR_MAP_BYTES)
+        xk = N.make_tensor_map(x_ptr, N.DT_F32, I, n_rows, I * 4, 32, 32)
+        xmn = N.make_tensor_map(x_ptr, N.DT_F32, I, n_rows, I * 4, 32, 32, mn_major=True)
+        C.memmove(C.addressof(m.xk), C.addressof(xk), N.TENSOR_MAP_BYTES)
+        C.memmove(C.addressof(m.xmn), C.addressof(xmn), N.TENSOR_MAP_BYTES)
+        return m
+
+    def _build_fused(self) -> None:
+        spec, cfg, lay = self.spec, self.cfg, self.layout
+        N.ensure_prepared(self.device)
+        I, H = spec.layer_sizes[0]
+        Cn = spec.num_classes
+        max_lanes = C.c_int(0)
+        N.check(self.lib.dm_fused_max_lanes(self.device, C.byref(max_lanes)), "fused occupancy")
+        lanes = max(1, min(cfg.lanes, max_lanes.value if max_lanes.value > 0 else cfg.lanes))
+        self.fused_lanes = lanes
+        out = C.c_void_p()
+        N.check(self.lib.dm_fexec_create(self.device, lanes, I, Cn, self.batch, C.byref(out)), "fused exec create")
+        self._fexec = out.value
+        xd, yd, xs, ys, ctl = (C.c_void_p() for _ in range(5))
+        slots = C.c_int(0)
+        N.check(self.lib.dm_fexec_buffers(self._fexec, C.byref(xd), C.byref(yd), C.byref(xs), C.byref(ys),
+                                          C.byref(ctl), C.byref(slots)))
+        self._fx_x_dev, self._fx_y_dev, self._fx_ctl, self._fx_slots = xd.value, yd.value, ctl.value, slots.value
+        self.x_bytes = N.FUSED_ROWS_PER_SLOT * I * 4
+        self.y_bytes = N.FUSED_ROWS_PER_SLOT * Cn * 4
+        names = spec.variable_names()
+        hb, wl, bl = lay.by_name[names[0][1]], lay.by_name[names[1][0]], lay.by_name[names[1][1]]
+        hw = lay.by_name[names[0][0]]
+        p = N.FusedParams()
+        p.B, p.H, p.C, p.I = self.batch, H, Cn, I
+        p.loss_kind = N.LOSS_BOOK if spec.loss == "book" else N.LOSS_XENT
+        p.ldw = hw.ld
+        p.strict = int(cfg.strict_steps)
+        # shards this worker pushes to, the global-step owner first (same order as the inbox entries)
+        order = list(self.inbox_order)
+        for k in range(self.cluster.num_ps):       # atomic mode has no inbox: every shard with items, in order
+            if k not in order and lay.shards[k].n_items > 0:
+                order.append(k)
+        if len(order) > N.FUSED_MAX_SHARDS:
+            raise ValueError(f"the fused engine talks to at most {N.FUSED_MAX_SHARDS} ps shards")
+        sidx = {k: i for i, k in enumerate(order)}
+        p.n_shards = len(order)
+        for i, k in enumerate(order):
+            p.shard[i].push = self._push_target(k, 0)
+            p.shard[i].inbox = (self.seg.addr("inbox", 8 * self.inbox_index[k])
+                                if (cfg.push_mode == "mailbox" and k in self.inbox_index) else None)
+        for sl in lay.fused_slices:
+            fs = p.slice[sl.rank]
+            fs.kc_begin, fs.kc_count, fs.shard, fs.flag_index, fs.w_offset = (sl.kc_begin, sl.kc_count, sidx[sl.ps],
+                                                                               sl.flag, sl.w_offset)
+        p.bias_h = self.ps_segs[hb.ps].addr("params", hb.offset * 4)
+        p.w_last = self.ps_segs[wl.ps].addr("params", wl.offset * 4)
+        p.b_last = self.ps_segs[bl.ps].addr("params", bl.offset * 4)
+        p.shard_bh, p.shard_wl, p.shard_bl = sidx[hb.ps], sidx[wl.ps], sidx[bl.ps]
+        p.flag_bh, p.flag_wl, p.flag_bl = hb.flag_base, wl.flag_base, bl.flag_base
+        p.off_bh, p.off_wl, p.off_bl = hb.offset, wl.offset, bl.offset
+        p.y_base = self._fx_y_dev
+        p.row_start, p.row_stride, p.row_wrap = 0, N.FUSED_ROWS_PER_SLOT, self._fx_slots * N.FUSED_ROWS_PER_SLOT
+        p.nslots = cfg.nslots
+        p.ps_global_step = (self.ps_segs[self.gs_owner].addr("ctrl", 4 * CTRL_GLOBAL_STEP)
+                            if cfg.push_mode == "atomic" else None)
+        if os.environ.get("DM_FUSED_DEBUG_TS") == "1":
+            self._fx_dbg = torch.zeros(64, dtype=torch.int64, device=f"cuda:{self.device}")
+            p.debug_ts = self._fx_dbg.data_ptr()
+        self._fx_params = p
+        self._fx_maps = self._fused_maps(self._fx_x_dev, self._fx_slots * N.FUSED_ROWS_PER_SLOT)
+        N.check(self.lib.dm_fexec_set_params(self._fexec, C.addressof(self._fx_maps), C.addressof(p)), "set params")
+        self._fx_ds_maps: Dict[Tuple[int, int], N.FusedMaps] = {}
+        self._fx_stage_x = torch.zeros(1, N.FUSED_ROWS_PER_SLOT, I, dtype=torch.float32)
+        self._fx_stage_y = torch.zeros(1, N.FUSED_ROWS_PER_SLOT, Cn, dtype=torch.float32)
+        self._fx_tickets: Dict[int, StepOutput] = {}
+        self._fx_ticket = 0
+        self.kernels_per_step = 1
+        torch.cuda.synchronize(self.device)
+
+    # ------------------------------------------------------------------------------------------
     # stepping
     # ------------------------------------------------------------------------------------------
     def submit(self, x: torch.Tensor, y: torch.Tensor) -> int:
         """Enqueue one training step on a host batch (x [B, in] float, y [B, classes] one-hot). Returns a ticket."""
         if self.cfg.backend != "cuda":
             raise RuntimeError("submit/result pipelining exists on the cuda backend; use step() on cpu")
+        if self.engine == "fused":
+            # the fused engine pipelines *inside* run_steps (chunks); a single submitted step runs to completion
+            out = self._fused_steps_host(x, y)
+            self._fx_ticket += 1
+            self._fx_tickets[self._fx_ticket] = out
+            if len(self._fx_tickets) > 4096:
+                self._fx_tickets.pop(next(iter(self._fx_tickets)))
+            return self._fx_ticket
         slot = C.c_int()
         N.check(self.lib.dm_exec_acquire_slot(self._exec, C.byref(slot)), "acquire slot")
         s = self._slots[slot.value]
@@ -483,6 +679,36 @@ class Worker:
         N.check(self.lib.dm_exec_submit(self._exec, s["x_stage_ptr"], s["y_stage_ptr"], C.byref(t)), "submit")
         return t.value
 
+    def set_lanes(self, lanes: int, strict: Optional[bool] = None) -> None:
+        """Fused engine: change the number of steps in flight (clusters per launch) and, optionally, the strict
+        read-your-writes pull order — e.g. `set_lanes(1, strict=True)` is the reference's sequential worker loop."""
+        if self.engine != "fused" or not self._fexec:
+            raise RuntimeError("set_lanes applies to a prepared fused engine")
+        if lanes < 1 or (self.cfg.push_mode == "mailbox" and lanes > self.cfg.nslots):
+            raise ValueError("lanes must be in [1, nslots]")
+        self.drain()
+        N.check(self.lib.dm_fexec_set_lanes(self._fexec, lanes), "set lanes")
+        self.fused_lanes = lanes
+        if strict is not None:
+            self._fx_params.strict = int(strict)
+            N.check(self.lib.dm_fexec_set_params(self._fexec, C.addressof(self._fx_maps), C.addressof(self._fx_params)),
+                    "set params")
+
+    def _fused_steps_host(self, x: torch.Tensor, y: torch.Tensor) -> StepOutput:
+        b = x.shape[0]
+        if b != self.batch:
+            raise ValueError(f"expected a batch of {self.batch}, got {b}")
+        self._fx_stage_x[0, :b].copy_(x.reshape(b, -1))
+        self._fx_stage_y[0, :b].copy_(y)
+        r = N.StepResult()
+        done = C.c_uint32(0)
+        N.check(self.lib.dm_fexec_steps_host(self._fexec, self._fx_stage_x.data_ptr(), self._fx_stage_y.data_ptr(), 1,
+                                             C.addressof(r), C.byref(done)), "fused step")
+        if done.value != 1:
+            raise N.NativeError("fused step did not run")
+        self._serve_local()
+        return StepOutput(r.loss, r.global_step, r.correct, r.seq)
+
     def submit_resident(self, x_ptr: int = 0, y_ptr: int = 0) -> int:
         """Enqueue a step whose inputs already live in device (or pinned) memory at x_ptr / y_ptr, laid out
         exactly like the slot buffers ([B_pad][ld_in] compute dtype, [B_pad][classes] fp32). 0 = reuse the
@@ -494,11 +720,24 @@ class Worker:
     def run_resident(self, n_steps: int, x_base_ptr: int, y_base_ptr: int, x_row_bytes: int, y_row_bytes: int,
                      n_rows: int, start: int = 0) -> None:
         """Native loop over a device-resident dataset: step i trains on rows ((start + i) * batch) % n_rows ..
-        (contiguous), copied device-to-device into the slot buffers. Results stay in the executor's history."""
+        (contiguous). Graph engine: copied device-to-device into the slot buffers; fused engine: one launch whose
+        TMA loads read the rows straight out of the dataset. Results stay in the executor."""
+        if self.engine == "fused":
+            if x_row_bytes != self.spec.in_features * 4 or y_row_bytes != self.spec.num_classes * 4:
+                raise ValueError("fused run_resident: dataset rows must be dense fp32 [in] / [classes]")
+            key = (x_base_ptr, n_rows)
+            if key not in self._fx_ds_maps:
+                self._fx_ds_maps[key] = self._fused_maps(x_base_ptr, n_rows + N.FUSED_ROWS_PER_SLOT)
+            N.check(self.lib.dm_fexec_run_resident(self._fexec, C.addressof(self._fx_ds_maps[key]), y_base_ptr,
+                                                   start * self.batch, self.batch, n_rows, n_steps), "run resident")
+            self._serve_local()
+            return
         N.check(self.lib.dm_exec_run_resident(self._exec, n_steps, x_base_ptr, y_base_ptr, x_row_bytes, y_row_bytes,
                                               n_rows, self.batch, start), "run resident")
 
     def result(self, ticket: int, wait: bool = True) -> Optional[StepOutput]:
+        if self.engine == "fused" and self.cfg.backend == "cuda":
+            return self._fx_tickets[ticket]
         r = N.StepResult()
         rc = self.lib.dm_exec_result(self._exec, ticket, C.addressof(r), int(wait))
         if rc == 1:
@@ -510,7 +749,11 @@ class Worker:
     def step(self, x: torch.Tensor, y: torch.Tensor) -> StepOutput:
         """One synchronous training step — the analogue of `sess.run([train_op, loss, global_step], feed_dict)`."""
         if self.cfg.backend == "cuda":
-            return self.result(self.submit(x, y), wait=True)
+            if self.engine == "fused":
+                return self._fused_steps_host(x, y)
+            out = self.result(self.submit(x, y), wait=True)
+            self._serve_local()
+            return out
         return self._cpu_step(x, y)
 
     def make_loader(self, images: torch.Tensor, labels: torch.Tensor, seed: int = 0, shuffle: bool = True):
@@ -530,18 +773,27 @@ class Worker:
             return out
         res = (N.StepResult * n_steps)()
         done = C.c_uint64()
-        N.check(self.lib.dm_exec_run(self._exec, loader.handle, n_steps, C.addressof(res), stop_at_global_step,
-                                     C.byref(done)), "exec run")
+        if self.engine == "fused":
+            N.check(self.lib.dm_fexec_run(self._fexec, loader.handle, n_steps, C.addressof(res), stop_at_global_step,
+                                          C.byref(done)), "fused exec run")
+        else:
+            N.check(self.lib.dm_exec_run(self._exec, loader.handle, n_steps, C.addressof(res), stop_at_global_step,
+                                         C.byref(done)), "exec run")
+        self._serve_local()
         raw = np.frombuffer(res, dtype=_STEP_DTYPE, count=n_steps)[: done.value]   # keeps `res` alive
         return StepOutputs(raw)
 
     def drain(self) -> None:
+        if self._fexec:
+            N.check(self.lib.dm_fexec_drain(self._fexec), "drain")
         if self._exec:
             N.check(self.lib.dm_exec_drain(self._exec), "drain")
 
     @property
     def compute_stream(self) -> int:
         """Raw cudaStream_t of the executor's compute stream (for CUDA-event timing of a run of steps)."""
+        if self._fexec:
+            return self.lib.dm_fexec_compute_stream(self._fexec)
         return self.lib.dm_exec_compute_stream(self._exec)
 
     def enqueue_wait_ack(self) -> None:
@@ -549,9 +801,10 @@ class Worker:
         far (mailbox mode). Used to close a device-timed region on the PS-side apply of its last step."""
         if self.cfg.backend != "cuda":
             return
-        N.check(self.lib.dm_exec_join(self._exec), "join lanes")   # lane 0 now follows every in-flight step
+        if self._exec:
+            N.check(self.lib.dm_exec_join(self._exec), "join lanes")   # lane 0 now follows every in-flight step
         if self.cfg.push_mode == "mailbox" and self.inbox_order:
-            N.check(self.lib.dm_launch_wait_ack(self.seg.addr("inbox"), len(self.inbox_order), self.seg.addr("seq"),
+            N.check(self.lib.dm_launch_wait_ack(self.seg.addr("inbox"), len(self.inbox_order), self._seq_word_ptr(),
                                                 self.compute_stream), "wait_ack")
 
     def fork_lanes(self) -> None:
@@ -560,6 +813,8 @@ class Worker:
             N.check(self.lib.dm_exec_fork(self._exec), "fork lanes")
 
     def kernel_launches(self) -> int:
+        if self._fexec:
+            return int(self.lib.dm_fexec_launches(self._fexec))
         return int(self.lib.dm_exec_kernel_launches(self._exec)) if self._exec else 0
 
     # ------------------------------------------------------------------------------------------
@@ -570,7 +825,7 @@ class Worker:
             self._views = []
             for k, seg in enumerate(self.ps_segs):
                 d = self.ps_desc[k]
-                arena, ni = d["arena_elems"], max(d["n_items"], 1)
+                arena, ni = d["arena_elems"], max(d.get("n_flags", d["n_items"]), 1)
                 w, ns = self.task_index, self.cfg.nslots
                 self._views.append({
                     "params": seg.tensor("params", torch.float32),
@@ -587,8 +842,16 @@ class Worker:
         # pull (X3): snapshot of the live shard memory; concurrent applies may tear it (Hogwild, like the reference)
         params = {}
         for name, vl in lay.by_name.items():
-            flat = views[vl.ps]["params"][vl.offset: vl.offset + vl.span]
-            params[name] = self._unpack(vl, flat)
+            if len({(pc.ps, pc.offset) for pc in vl.pieces}) == 1:
+                flat = views[vl.ps]["params"][vl.offset: vl.offset + vl.span]
+                params[name] = self._unpack(vl, flat)
+            else:   # column-split variable: every owning shard holds the live values of its own columns
+                full = torch.empty(vl.rows, vl.cols)
+                for pc in vl.pieces:
+                    if pc.c1 > pc.c0:
+                        src = self._unpack(vl, views[pc.ps]["params"][pc.offset: pc.offset + vl.span])
+                        full[:, pc.c0:pc.c1] = src[:, pc.c0:pc.c1]
+                params[name] = full
         loss, grads, logits = mlp.manual_loss_and_grads(self.spec, params, x.float(), y.float())
         correct = mlp.accuracy_count(logits, y)
         self._seq_host += 1
@@ -600,11 +863,13 @@ class Worker:
                     raise TimeoutError(f"ps {k} did not acknowledge push {seq - ns}")
         # push (X4): gradients into our mailbox slot, then publish every item's flag
         for name, vl in lay.by_name.items():
-            views[vl.ps]["mailbox"][slot, vl.offset: vl.offset + vl.span] = self._pack(vl, grads[name])
+            packed = self._pack(vl, grads[name])
+            for k, off in dict.fromkeys((pc.ps, pc.offset) for pc in vl.pieces):
+                views[k]["mailbox"][slot, off: off + vl.span] = packed
         for k in self.inbox_order:
             v = views[k]
-            for item in range(lay.shards[k].n_items):
-                self.lib.dm_store_release_u32(v["flags_addr"] + 4 * (slot * v["ni"] + item), seq)
+            for flag in range(lay.shards[k].n_flags):
+                self.lib.dm_store_release_u32(v["flags_addr"] + 4 * (slot * v["ni"] + flag), seq)
         if self.inbox_order:
             ack = self.lib.dm_load_acquire_u32(self._inbox_addr)
             gstep = self.lib.dm_load_acquire_u32(self._inbox_addr + 4) + (seq - ack)
@@ -618,6 +883,18 @@ class Worker:
     def evaluate(self, images: torch.Tensor, labels: torch.Tensor) -> Tuple[float, float]:
         """(mean loss, accuracy) of the current PS variables on a host dataset; GPU path uses the hand-written
         accuracy reduction kernel on torch-computed logits of the pulled variables."""
+        if self.cfg.backend == "cuda" and self.engine == "fused":
+            # forward on the pulled variables with torch, correct-prediction count with the hand-written accuracy
+            # reduction (SURVEY K12); evaluation is not part of a training step
+            self.drain()
+            dev = f"cuda:{self.device}"
+            params = {k: v.to(dev) for k, v in self.read_variables().items()}
+            xs, ys = images.float().to(dev), labels.float().to(dev).contiguous()
+            logits, _ = mlp.forward_logits(self.spec, params, xs)
+            logits = logits.float().contiguous()
+            correct = int(head_ops.accuracy_count(logits, ys).item())
+            loss = float(mlp.loss_from_logits(self.spec, logits, ys))
+            return loss, correct / max(1, images.shape[0])
         if self.cfg.backend == "cuda":
             # forward tcgen05 GEMMs (weights pulled from the PS shards) + the head kernel in eval mode; whole
             # batches only (the step kernels are specialised for this worker's batch size).
@@ -659,15 +936,17 @@ class Worker:
         self._finished = True
         w = self.task_index
         if self.cfg.push_mode == "mailbox":
-            if self.cfg.backend == "cuda" and self._exec:
+            # every shard hears it, also one that owns no variable (its serve loop only waits for this word)
+            if self.cfg.backend == "cuda" and (self._exec or self._fexec):
                 self.drain()
-                stream = self.lib.dm_exec_compute_stream(self._exec)
-                for k in self.inbox_order:
+                stream = self.compute_stream
+                for k in range(self.cluster.num_ps):
                     N.check(self.lib.dm_launch_worker_done(self.ps_segs[k].addr("ctrl", 4 * (CTRL_WORKER_DONE + w)),
-                                                           self.seg.addr("seq"), stream))
+                                                           self._seq_word_ptr(), stream))
                 N.check(self.lib.dm_stream_sync(stream))
+                self._serve_local()
             elif self.cfg.backend == "cpu":
-                for k in self.inbox_order:
+                for k in range(self.cluster.num_ps):
                     self.lib.dm_store_release_u32(self.ps_segs[k].addr("ctrl", 4 * (CTRL_WORKER_DONE + w)),
                                                   self._seq_host + 1)
         self.rdv.put(f"session/done/{w}", 1)
@@ -677,10 +956,15 @@ class Worker:
         if self._closed:
             return
         self._closed = True
+        if getattr(self, "_hb_thread", None) is not None:
+            self._hb_stop.set()
         self.finish()
         if self._exec:
             self.lib.dm_exec_destroy(self._exec)
             self._exec = None
+        if self._fexec:
+            self.lib.dm_fexec_destroy(self._fexec)
+            self._fexec = None
         self._views = None
         for seg in self.ps_segs:
             seg.close()

@@ -47,8 +47,8 @@ class InProcessCluster:
         base = free_port()
         ports = [base] + [free_port() for _ in range(num_ps)]
         self.cluster = ClusterSpec(tuple(f"127.0.0.1:{p}" for p in ports[:num_ps]), (f"127.0.0.1:{ports[-1]}",))
-        self.ps: List[ParameterServer] = [ParameterServer(self.cluster, k, spec, opt, cfg, device=device)
-                                          for k in range(num_ps)]
+        self.ps: List[ParameterServer] = [ParameterServer(self.cluster, k, spec, opt, cfg, device=device,
+                                                          batch_size=batch_size) for k in range(num_ps)]
         self.worker = Worker(self.cluster, 0, spec, opt, cfg, batch_size=batch_size, device=device)
         self.worker.connect()
         self.worker.prepare()
@@ -63,6 +63,7 @@ class InProcessCluster:
             self.worker.initialize_variables(seed=seed, params=params)
         for ps in self.ps:
             ps.start()
+        self.worker.attach_local_ps(self.ps)   # one-shot ps tasks are served by the worker after every launch
         self.worker.wait_ready()
 
     def close(self) -> None:

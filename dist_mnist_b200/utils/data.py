@@ -83,7 +83,16 @@ def load_mnist(data_dir: Optional[str]) -> Optional[Dataset]:
 
 
 def get_dataset(data_dir: Optional[str], n: int = TRAIN_SIZE, seed: int = 0) -> Dataset:
-    return load_mnist(data_dir) or synthetic_mnist(n=n, seed=seed)
+    """`--data_dir` given: the idx files must be there (the reference always trains on real MNIST, DS:69) — a typo
+    must not silently turn into training on synthetic data. No `--data_dir`: synthetic 28x28 data (no network)."""
+    if data_dir is not None:
+        ds = load_mnist(data_dir)
+        if ds is None:
+            raise FileNotFoundError(
+                f"--data_dir {data_dir!r} does not contain the MNIST training idx files "
+                f"(train-images-idx3-ubyte[.gz], train-labels-idx1-ubyte[.gz]); omit --data_dir for synthetic data")
+        return ds
+    return synthetic_mnist(n=n, seed=seed)
 
 
 class BatchIterator:

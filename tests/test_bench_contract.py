@@ -23,10 +23,13 @@ def test_graft_entry_build():
 def test_bench_defaults_and_config_are_consistent():
     sys.path.insert(0, ROOT)
     import bench
-    from dist_mnist_b200.parallel.config import EngineConfig, OptimizerConfig
+    from dist_mnist_b200.models import mlp
+    from dist_mnist_b200.parallel.config import OptimizerConfig
     a = bench.parse_args([])
     assert a.gpus == 1 and a.steps >= 100 and a.warmup >= 3 and a.optimizer == "adam" and a.batch_size == 32
-    # the defaults bench.py derives (nslots = lanes, U = min(lanes, 4), ring = 2 x lanes) must validate
-    lanes = a.lanes
-    EngineConfig(backend="cuda", lanes=lanes, graph_steps=a.graph_steps or min(lanes, 4), nslots=a.nslots or max(2, lanes),
-                 pipeline_slots=max(4, 2 * lanes)).validate(OptimizerConfig("adam", 1e-4))
+    # the configuration bench.py derives from its defaults must validate and select the fused engine for the
+    # reference's live model (784-100-10, batch 32)
+    cfg = bench.engine_config(a)
+    cfg.validate(OptimizerConfig("adam", 1e-4))
+    assert cfg.nslots >= cfg.lanes
+    assert cfg.resolve_engine(mlp.get_model(a.model, a.hidden_units), a.batch_size) == "fused"
