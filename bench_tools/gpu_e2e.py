@@ -47,15 +47,25 @@ def wait_gstep(worker, target, timeout=10.0):
 # error directly reflects kernel numerics (tf32 / bf16 rounding); Adam's normalised step m/sqrt(v) turns a
 # rounding-level gradient difference on a near-zero gradient into a full +-lr step, hence the looser bound there.
 TRAJ_CASES = [
+        # --- fused step engine (the reference's live configuration: 784-100-10, batch 32, fp32) ---
         ("book", "adam", "fp32", "mailbox", 1, 32, 5e-2),
         ("book", "sgd", "fp32", "mailbox", 1, 32, 2e-2),
         ("book", "sgd", "fp32", "atomic", 1, 32, 2e-2),
         ("book", "adam", "fp32", "mailbox", 2, 32, 5e-2),
+        # --- per-layer kernels in a CUDA graph (deeper / wider / bf16 models) ---
         ("zhihu", "sgd", "fp32", "mailbox", 2, 100, 2e-2),
         ("zhihu", "adam", "fp32", "mailbox", 2, 100, 2.5e-1),
         ("wide", "sgd", "bf16", "mailbox", 2, 64, 5e-2),
         ("wide", "adam", "bf16", "mailbox", 2, 64, 2.5e-1),
         ("book", "adam", "bf16", "mailbox", 1, 32, 2e-1),
+        # --- fused engine: intra-variable (row-split) sharding over 2 and 8 ps shards, strict pull order, xent loss,
+        #     a partial batch and a narrower hidden layer ---
+        ("book", "sgd", "fp32", "mailbox", 2, 32, 2e-2, {"sharding": "row_split"}),
+        ("book", "adam", "fp32", "mailbox", 8, 32, 5e-2, {"sharding": "row_split", "strict_steps": True}),
+        ("book", "sgd", "fp32", "mailbox", 1, 20, 2e-2, {"loss": "xent", "hidden": 64}),
+        # --- the same flagship model through the graph engine (kept as the general path) ---
+        ("book", "adam", "fp32", "mailbox", 1, 32, 5e-2, {"engine": "graph"}),
+        ("book", "sgd", "fp32", "atomic", 1, 32, 2e-2, {"engine": "graph"}),
 ]
 
 
@@ -63,13 +73,18 @@ def check_traj(only=None) -> bool:
     ok = True
     ds = data.synthetic_mnist(4096, seed=3)
     cases = TRAJ_CASES if only is None else [TRAJ_CASES[only]]
-    for (model, okind, dtype, push, nps, batch, tol) in cases:
-        name = f"traj model={model} opt={okind} dtype={dtype} push={push} ps={nps} B={batch}"
+    for case in cases:
+        (model, okind, dtype, push, nps, batch, tol), extra = case[:7], (case[7] if len(case) > 7 else {})
+        name = f"traj model={model} opt={okind} dtype={dtype} push={push} ps={nps} B={batch} {extra or ''}"
         try:
-            spec = mlp.get_model(model)
+            spec = mlp.get_model(model, extra.get("hidden", 100)) if model == "book" else mlp.get_model(model)
+            if extra.get("loss"):
+                import dataclasses
+                spec = dataclasses.replace(spec, loss=extra["loss"])
             lr = 1e-3 if okind == "adam" else 5e-2
             opt = OptimizerConfig(okind, lr)
-            cfg = EngineConfig(backend="cuda", dtype=dtype, push_mode=push, sharding="round_robin")
+            cfg = EngineConfig(backend="cuda", dtype=dtype, push_mode=push, sharding=extra.get("sharding", "round_robin"),
+                               engine=extra.get("engine", "auto"), strict_steps=extra.get("strict_steps", False))
             params = mlp.init_params(spec, seed=7)
             ref_p = {k: t.clone() for k, t in params.items()}
             ref_m = {k: torch.zeros_like(t) for k, t in params.items()}
@@ -98,8 +113,8 @@ def check_traj(only=None) -> bool:
                 gs = w.read_global_step()
                 acc_loss, acc = w.evaluate(ds.images[:512], ds.labels[:512])
             good = worst < tol and perr < tol and gs == n_steps
-            print(f"[{'PASS' if good else 'FAIL'}] {name}: worst_loss_rel={worst:.2e} param_rel={perr:.2e} "
-                  f"global_step={gs} eval_loss={acc_loss:.4f} acc={acc:.3f}", flush=True)
+            print(f"[{'PASS' if good else 'FAIL'}] {name}: engine={w.engine} worst_loss_rel={worst:.2e} "
+                  f"param_rel={perr:.2e} global_step={gs} eval_loss={acc_loss:.4f} acc={acc:.3f}", flush=True)
             ok &= good
         except Exception:
             traceback.print_exc()
@@ -145,10 +160,21 @@ def check_throughput(only=None) -> bool:
     return ok
 
 
-PIPE_CASES = [("book", "adam", "fp32", "mailbox", 2, 1, False), ("book", "adam", "fp32", "mailbox", 4, 2, True),
-              ("book", "adam", "fp32", "mailbox", 4, 2, True, True),      # classifier head fused into the forward GEMM
-              ("book", "sgd", "fp32", "atomic", 4, 4, True), ("wide", "adam", "bf16", "mailbox", 4, 2, True),
-              ("zhihu", "sgd", "fp32", "mailbox", 2, 2, False)]
+PIPE_CASES = [
+    # graph engine (lanes / group graphs / PDL)
+    ("book", "adam", "fp32", "mailbox", 2, 1, False, False, {"engine": "graph"}),
+    ("book", "adam", "fp32", "mailbox", 4, 2, True, False, {"engine": "graph"}),
+    ("book", "adam", "fp32", "mailbox", 4, 2, True, True, {"engine": "graph"}),   # head fused into the forward GEMM
+    ("book", "sgd", "fp32", "atomic", 4, 4, True, False, {"engine": "graph"}),
+    ("wide", "adam", "bf16", "mailbox", 4, 2, True),
+    ("zhihu", "sgd", "fp32", "mailbox", 2, 2, False),
+    # fused engine: lanes = clusters of one launch, chunked executor
+    ("book", "adam", "fp32", "mailbox", 1, 1, True, False, {}),
+    ("book", "adam", "fp32", "mailbox", 8, 1, True, False, {}),
+    ("book", "sgd", "fp32", "atomic", 4, 1, True, False, {}),
+    ("book", "adam", "fp32", "mailbox", 8, 1, True, False, {"sharding": "row_split", "num_ps": 2}),
+    ("book", "adam", "fp32", "mailbox", 2, 1, True, False, {"strict_steps": True}),
+]
 
 
 def check_pipelined(only=None) -> bool:
@@ -160,14 +186,17 @@ def check_pipelined(only=None) -> bool:
     ds = data.synthetic_mnist(8192, seed=0)
     for case in (PIPE_CASES if only is None else [PIPE_CASES[only]]):
         (model, okind, dtype, push, lanes, gsteps, pdl), fuse = case[:7], (len(case) > 7 and case[7])
+        extra = case[8] if len(case) > 8 else {}
         name = (f"pipelined model={model} opt={okind} dtype={dtype} push={push} lanes={lanes} graph_steps={gsteps} "
-                f"pdl={pdl} fuse_head={fuse}")
+                f"pdl={pdl} fuse_head={fuse} {extra or ''}")
         try:
             spec = mlp.get_model(model)
             opt = OptimizerConfig(okind, 1e-3 if okind == "adam" else 1e-2)
             cfg = EngineConfig(backend="cuda", dtype=dtype, push_mode=push, lanes=lanes, graph_steps=gsteps,
-                               nslots=max(2, lanes), pipeline_slots=max(4, 2 * lanes), pdl=pdl, fuse_head=fuse)
-            with InProcessCluster(spec, opt, cfg, batch_size=32) as cl:
+                               nslots=max(2, lanes), pipeline_slots=max(4, 2 * lanes), pdl=pdl, fuse_head=fuse,
+                               engine=extra.get("engine", "auto"), sharding=extra.get("sharding", "round_robin"),
+                               strict_steps=extra.get("strict_steps", False))
+            with InProcessCluster(spec, opt, cfg, batch_size=32, num_ps=extra.get("num_ps", 1)) as cl:
                 w = cl.worker
                 loader = w.make_loader(ds.images, ds.labels, seed=0)
                 outs = []
@@ -188,7 +217,7 @@ def check_pipelined(only=None) -> bool:
                     good_fused = True
                 good = (good_fused and len(outs) == total and gs == total and seqs == list(range(1, total + 1))
                         and last < first and all(o.loss == o.loss for o in outs))
-                print(f"[{'PASS' if good else 'FAIL'}] {name}: steps={len(outs)} global_step={gs} "
+                print(f"[{'PASS' if good else 'FAIL'}] {name}: engine={w.engine} steps={len(outs)} global_step={gs} "
                       f"seqs unique={seqs == list(range(1, total + 1))} loss {first:.4f} -> {last:.4f}", flush=True)
                 ok &= good
         except Exception:

@@ -1,5 +1,6 @@
-"""Per-kernel SASS mnemonic evidence of the in-tree library (no GPU needed): `python -m bench_tools.sass_summary`
-rewrites profiles/sass/mnemonic_summary.txt from `cuobjdump -sass dist_mnist_b200/libdmnist_sm100a.so`."""
+"""Per-kernel SASS evidence of the in-tree library (no GPU needed): `python -m bench_tools.sass_summary` rewrites
+profiles/sass/mnemonic_summary.txt (mnemonic histogram per kernel) and profiles/sass/listings/<kernel>.sass (the full
+`cuobjdump -sass` listing of every kernel, one file each) from dist_mnist_b200/libdmnist_sm100a.so."""
 import collections
 import re
 import subprocess
@@ -23,6 +24,39 @@ def main() -> int:
     txt = subprocess.run(["cuobjdump", "-sass", str(lib)], capture_output=True, text=True, check=True).stdout
     out = [HEADER]
     name, counts, n = None, None, 0
+    # ---- full listings, one file per kernel (demangled name in the header, mangled name in the file name) ----
+    ldir = ROOT / "profiles" / "sass" / "listings"
+    ldir.mkdir(parents=True, exist_ok=True)
+    for old in ldir.glob("*.sass"):
+        old.unlink()
+    cur_name, cur_lines, n_files = None, [], 0
+
+    def flush_listing():
+        nonlocal n_files
+        if cur_name:
+            dem = subprocess.run(["c++filt", cur_name], capture_output=True, text=True).stdout.strip() or cur_name
+            short = re.sub(r"[^A-Za-z0-9_]+", "_", dem.split("(")[0])[:120]
+            body = "\n".join(cur_lines)
+            (ldir / f"{short}.sass").write_text(f"// {dem}\n// {cur_name}  (sm_100a, cuobjdump -sass)\n{body}\n")
+            n_files += 1
+
+    for line in txt.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            flush_listing()
+            cur_name, cur_lines = m.group(1), []
+            continue
+        if cur_name:
+            # keep the instruction text, drop the encoding words (halves the size, loses nothing readable)
+            mm = re.match(r"(\s+/\*[0-9a-f]{4}\*/\s+.*?;)\s+/\* 0x[0-9a-f]+ \*/", line)
+            if mm:
+                cur_lines.append(mm.group(1))
+            elif re.match(r"\s+/\* 0x[0-9a-f]+ \*/\s*$", line):
+                continue
+            elif line.strip():
+                cur_lines.append(line.rstrip())
+    flush_listing()
+    print(f"wrote {n_files} listings under {ldir}")
 
     def flush():
         if name:

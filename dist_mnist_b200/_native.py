@@ -270,6 +270,7 @@ def _declare(l: C.CDLL) -> None:
         "dm_fexec_set_lanes": (i, [vp, i]),
         "dm_fexec_gather_threads": (i, [vp]),
         "dm_fexec_drain": (i, [vp]),
+        "dm_fexec_debug": (i, [vp, vp]),
         "dm_fexec_steps_host": (i, [vp, vp, vp, u32, vp, C.POINTER(u32)]),
         "dm_fexec_run": (i, [vp, vp, u64, vp, u32, C.POINTER(u64)]),
         "dm_fexec_run_resident": (i, [vp, vp, vp, u64, u64, u64, u64]),

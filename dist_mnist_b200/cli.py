@@ -103,6 +103,9 @@ def build_parser() -> argparse.ArgumentParser:
                         "it (0 = never, like the reference)")
     p.add_argument("--inject_fault", type=int, default=0,
                    help="worker: crash (os._exit) after this many local steps — fault-injection hook for tests")
+    p.add_argument("--chunk_sleep", type=float, default=0.0,
+                   help="worker: sleep this many seconds after every chunk of 50 steps — slows a worker down (tests of "
+                        "the failure / restart path need a run that outlives a crash and a restart)")
     p.add_argument("--ps_exit_when_done", action="store_true",
                    help="let a ps task return once every worker has finished (reference ps blocks forever)")
     p.add_argument("--rendezvous_timeout", type=float, default=300.0)
@@ -157,6 +160,11 @@ def run(args: argparse.Namespace) -> int:
         except KeyboardInterrupt:
             pass
         finally:
+            try:
+                print(f"[ps {args.task_index}] exiting: global_step={ps.global_step()} "
+                      f"owns_global_step={int(ps.shard.owns_global_step)} items={ps.shard.n_items}", flush=True)
+            except Exception:
+                pass
             ps.close()
         return 0
 
@@ -182,9 +190,12 @@ def run(args: argparse.Namespace) -> int:
         metrics = TrainMetricsWriter(args.metrics_file, args.task_index, args.batch_size,
                                      every_steps=max(1, args.log_every), echo=args.log_steps_per_sec)
     try:
-        train_loop(worker, dataset, train_steps=args.train_steps, log_every=args.log_every,
-                   checkpoint_dir=args.checkpoint_dir, save_checkpoint_secs=args.save_checkpoint_secs,
-                   seed=args.seed, inject_fault_after=args.inject_fault, metrics=metrics)
+        res = train_loop(worker, dataset, train_steps=args.train_steps, log_every=args.log_every,
+                         checkpoint_dir=args.checkpoint_dir, save_checkpoint_secs=args.save_checkpoint_secs,
+                         seed=args.seed, inject_fault_after=args.inject_fault, metrics=metrics,
+                         chunk_sleep_s=args.chunk_sleep)
+        print(f"[worker {args.task_index}] done: local_steps={res.steps_run} last_global_step={res.last_global_step} "
+              f"engine={worker.engine}", flush=True)
     finally:
         if metrics is not None:
             metrics.close()

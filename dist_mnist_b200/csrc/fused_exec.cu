@@ -142,10 +142,14 @@ struct FusedExec {
   dm::StepResult* res_big = nullptr;      // pinned, grown on demand (run_resident / single steps)
   size_t res_big_cap = 0;
   uint32_t* ctl_dev = nullptr;            // [0] step counter, [1] stop word, [2] seq word (pushes made)
+  uint32_t* zeros_pin = nullptr;          // pinned zeros: control words are reset with a DMA copy, never a memset —
+                                          // a memset may be a driver kernel whose lazy first load deadlocks against
+                                          // a resident persistent ps kernel
   cudaStream_t compute = nullptr, copy = nullptr;
   dm::FusedMaps maps{};
   dm::FusedParams params{};
   bool have_params = false;
+  bool warmed = false;
   uint64_t steps_done = 0;    // steps completed over the executor's lifetime == push sequence numbers used
   uint64_t launches = 0;
   ChunkBuf bufs[kBuffers];
@@ -163,7 +167,7 @@ struct FusedExec {
     p.stop_word = ctl_dev + 1;
     p.seq_word = ctl_dev + 2;
     p.results = results;
-    FX_CUDA(cudaMemsetAsync(ctl_dev, 0, reset_stop ? 8 : 4, compute));
+    FX_CUDA(cudaMemcpyAsync(ctl_dev, zeros_pin, reset_stop ? 8 : 4, cudaMemcpyHostToDevice, compute));
     FX_CUDA(dm::launch_fused_step(m, p, lanes, compute));
     ++launches;
     return 0;
@@ -216,6 +220,8 @@ int dm_fexec_create(int device, int lanes, int I, int C, int batch, void** out) 
   memset(ex->res_chunks, 0, slots * sizeof(dm::StepResult));
   FX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ex->ctl_dev), 64));
   FX_CUDA(cudaMemset(ex->ctl_dev, 0, 64));
+  FX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ex->zeros_pin), 64, cudaHostAllocDefault));
+  memset(ex->zeros_pin, 0, 64);
   FX_CUDA(cudaStreamCreateWithFlags(&ex->compute, cudaStreamNonBlocking));
   FX_CUDA(cudaStreamCreateWithFlags(&ex->copy, cudaStreamNonBlocking));
   for (auto& b : ex->bufs) {
@@ -249,6 +255,16 @@ int dm_fexec_set_params(void* h, const void* maps, const void* params) {
   memcpy(&ex->maps, maps, sizeof(dm::FusedMaps));
   memcpy(&ex->params, params, sizeof(dm::FusedParams));
   ex->have_params = true;
+  // Dry launch (0 steps: every cluster finds nothing to claim and exits). The first real launch of a kernel can make
+  // the driver allocate per-context resources (local-memory pool for its stack frame, the device printf FIFO, cluster
+  // launch state), which needs a context-wide synchronisation — and would deadlock once a persistent ps kernel is
+  // resident on this GPU. Callers set the launch template before any ps kernel is started (Worker.prepare()).
+  if (!ex->warmed) {
+    if (ex->launch(ex->maps, ex->params, 0, ex->res_chunks, 0, true) != 0) return -1;
+    FX_CUDA(cudaStreamSynchronize(ex->compute));
+    --ex->launches;
+    ex->warmed = true;
+  }
   return 0;
 }
 
@@ -263,6 +279,27 @@ int dm_fexec_set_lanes(void* h, int lanes) {
   return 0;
 }
 int dm_fexec_gather_threads(void* h) { return static_cast<FusedExec*>(h)->n_threads; }
+
+// Debug aid (hang analysis): control words {step counter, stop word, pushes made} read through a side stream while
+// kernels may be running, plus seq / global_step of the first result slot of the chunk ring.
+int dm_fexec_debug(void* h, uint32_t* out8) {
+  FusedExec* ex = static_cast<FusedExec*>(h);
+  cudaStream_t s;
+  FX_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  uint32_t* pin = nullptr;
+  FX_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&pin), 64, cudaHostAllocDefault));
+  FX_CUDA(cudaMemcpyAsync(pin, ex->ctl_dev, 16, cudaMemcpyDeviceToHost, s));
+  FX_CUDA(cudaStreamSynchronize(s));
+  for (int i = 0; i < 4; ++i) out8[i] = pin[i];
+  out8[4] = ex->res_chunks[0].seq;
+  out8[5] = ex->res_chunks[0].global_step;
+  out8[6] = static_cast<uint32_t>(ex->steps_done);
+  out8[7] = cudaStreamQuery(ex->compute) == cudaSuccess ? 0u : 1u;
+  cudaGetLastError();
+  cudaFreeHost(pin);
+  cudaStreamDestroy(s);
+  return 0;
+}
 
 int dm_fexec_drain(void* h) {
   FusedExec* ex = static_cast<FusedExec*>(h);
@@ -498,6 +535,7 @@ int dm_fexec_destroy(void* h) {
   cudaFreeHost(ex->x_stage);
   cudaFreeHost(ex->y_stage);
   cudaFreeHost(ex->res_chunks);
+  cudaFreeHost(ex->zeros_pin);
   if (ex->res_big) cudaFreeHost(ex->res_big);
   cudaStreamDestroy(ex->compute);
   cudaStreamDestroy(ex->copy);

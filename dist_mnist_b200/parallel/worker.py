@@ -649,6 +649,12 @@ class Worker:
         self._fx_stage_y = torch.zeros(1, N.FUSED_ROWS_PER_SLOT, Cn, dtype=torch.float32)
         self._fx_tickets: Dict[int, StepOutput] = {}
         self._fx_ticket = 0
+        # evaluation buffers (allocated now: nothing is allocated once a persistent ps kernel may be resident)
+        self._ev_rows = 4096
+        self._ev_dev = torch.zeros(2 * self._ev_rows, Cn, dtype=torch.float32, device=f"cuda:{self.device}")
+        self._ev_cnt = torch.zeros(1, dtype=torch.int32, device=f"cuda:{self.device}")
+        self._ev_pin = torch.zeros(2 * self._ev_rows, Cn, dtype=torch.float32).pin_memory()
+        self._ev_cnt_pin = torch.zeros(1, dtype=torch.int32).pin_memory()
         self.kernels_per_step = 1
         torch.cuda.synchronize(self.device)
 
@@ -884,16 +890,33 @@ class Worker:
         """(mean loss, accuracy) of the current PS variables on a host dataset; GPU path uses the hand-written
         accuracy reduction kernel on torch-computed logits of the pulled variables."""
         if self.cfg.backend == "cuda" and self.engine == "fused":
-            # forward on the pulled variables with torch, correct-prediction count with the hand-written accuracy
-            # reduction (SURVEY K12); evaluation is not part of a training step
+            # Evaluation is not part of a training step: logits of the pulled variables are computed with torch on the
+            # host (no torch CUDA kernel is launched — a lazily loaded kernel could deadlock against a resident
+            # persistent ps kernel of an in-process cluster), the correct-prediction count with the hand-written,
+            # pre-loaded accuracy reduction (SURVEY K12) on pre-allocated device buffers.
             self.drain()
-            dev = f"cuda:{self.device}"
-            params = {k: v.to(dev) for k, v in self.read_variables().items()}
-            xs, ys = images.float().to(dev), labels.float().to(dev).contiguous()
-            logits, _ = mlp.forward_logits(self.spec, params, xs)
+            params = self.read_variables()
+            logits, _ = mlp.forward_logits(self.spec, params, images.float())
             logits = logits.float().contiguous()
-            correct = int(head_ops.accuracy_count(logits, ys).item())
-            loss = float(mlp.loss_from_logits(self.spec, logits, ys))
+            labels_f = labels.float().contiguous()
+            loss = float(mlp.loss_from_logits(self.spec, logits, labels_f))
+            stream = self.compute_stream
+            Cn, cap = self.spec.num_classes, self._ev_rows
+            correct = 0
+            for r0 in range(0, logits.shape[0], cap):
+                n = min(cap, logits.shape[0] - r0)
+                self._ev_pin[:n].copy_(logits[r0:r0 + n])
+                self._ev_pin[cap:cap + n].copy_(labels_f[r0:r0 + n])
+                self._ev_cnt_pin.zero_()
+                N.check(self.lib.dm_memcpy_async(self._ev_dev.data_ptr(), self._ev_pin.data_ptr(), n * Cn * 4, stream))
+                N.check(self.lib.dm_memcpy_async(self._ev_dev.data_ptr() + cap * Cn * 4,
+                                                 self._ev_pin.data_ptr() + cap * Cn * 4, n * Cn * 4, stream))
+                N.check(self.lib.dm_memcpy_async(self._ev_cnt.data_ptr(), self._ev_cnt_pin.data_ptr(), 4, stream))
+                N.check(self.lib.dm_launch_accuracy(self._ev_dev.data_ptr(), self._ev_dev.data_ptr() + cap * Cn * 4, n, Cn,
+                                                    self._ev_cnt.data_ptr(), stream), "accuracy kernel")
+                N.check(self.lib.dm_memcpy_async(self._ev_cnt_pin.data_ptr(), self._ev_cnt.data_ptr(), 4, stream))
+                N.check(self.lib.dm_stream_sync(stream))
+                correct += int(self._ev_cnt_pin.item())
             return loss, correct / max(1, images.shape[0])
         if self.cfg.backend == "cuda":
             # forward tcgen05 GEMMs (weights pulled from the PS shards) + the head kernel in eval mode; whole

@@ -93,7 +93,8 @@ class TrainLoopResult:
 def train_loop(worker: Worker, dataset: Dataset, train_steps: int = 4000, log_every: int = 100,
                checkpoint_dir: Optional[str] = None, save_checkpoint_secs: float = 600.0, seed: int = 0,
                chunk: int = 50, print_fn: Callable[[str], None] = print,
-               inject_fault_after: int = 0, metrics: Optional[TrainMetricsWriter] = None) -> TrainLoopResult:
+               inject_fault_after: int = 0, metrics: Optional[TrainMetricsWriter] = None,
+               chunk_sleep_s: float = 0.0) -> TrainLoopResult:
     """The worker's `MonitoredTrainingSession` loop (DS:106-116).
 
     Runs until a step reports `global_step >= train_steps` (StopAtStepHook on the shared counter), printing
@@ -128,6 +129,8 @@ def train_loop(worker: Worker, dataset: Dataset, train_steps: int = 4000, log_ev
                 stop = True
         if not outs:
             break
+        if chunk_sleep_s > 0:
+            time.sleep(chunk_sleep_s)
         if worker.is_chief and checkpoint_dir and time.time() - last_save >= save_checkpoint_secs:
             ckpt_path = ckpt_utils.save_checkpoint(worker, checkpoint_dir)
             last_save = time.time()
