@@ -60,7 +60,7 @@ def parse_args(argv=None):
     p.add_argument("--num_ps", type=int, default=1)
     p.add_argument("--sharding", choices=["round_robin", "byte_balanced", "row_split"], default="round_robin")
     p.add_argument("--engine", choices=["auto", "fused", "graph"], default="auto")
-    p.add_argument("--nslots", type=int, default=0, help="mailbox slots per worker (0 = 2 x lanes)")
+    p.add_argument("--nslots", type=int, default=0, help="mailbox slots per worker (0 = max(4 x lanes, 8))")
     p.add_argument("--lanes", type=int, default=8,
                    help="steps of one worker in flight on its GPU at once (async SGD; must be <= nslots)")
     p.add_argument("--strict_steps", action="store_true")
@@ -77,7 +77,7 @@ def engine_config(args, backend: str = "cuda"):
     from dist_mnist_b200.parallel.config import EngineConfig
 
     lanes = max(1, args.lanes)
-    return EngineConfig(backend=backend, dtype=args.dtype, nslots=args.nslots or 2 * lanes, apply_mode=args.apply_mode,
+    return EngineConfig(backend=backend, dtype=args.dtype, nslots=args.nslots or max(4 * lanes, 8), apply_mode=args.apply_mode,
                         push_mode=args.push_mode, sharding=args.sharding, lanes=lanes,
                         graph_steps=args.graph_steps or min(lanes, 4), pipeline_slots=max(4, 2 * lanes),
                         engine=args.engine, strict_steps=args.strict_steps, ps_row_blocks=args.ps_row_blocks)
@@ -127,6 +127,10 @@ def main(argv=None) -> int:
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL builds its communicator lazily inside the first collective (hundreds of milliseconds): do that now, not
+        # inside the barrier that precedes the first timed region (the NVLink sublinks would fall asleep meanwhile)
+        dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
 
     spec = mlp.get_model(args.model, args.hidden_units)
     opt = OptimizerConfig(args.optimizer, args.learning_rate)
@@ -195,6 +199,7 @@ def main(argv=None) -> int:
 
     rdv_any = worker.rdv if worker is not None else ps_list[0].rdv
     phase = [0]
+    sync_ms = []
 
     def full_sync(restart: bool = True):
         """barrier + torch.cuda.synchronize() on every rank.
@@ -204,15 +209,19 @@ def main(argv=None) -> int:
         against it. So: workers quiesce (all their pushes acknowledged) and say so through the TCP store; ps tasks
         then stop their serve kernel (all shard state stays in HBM); only then does every rank run the NCCL
         barrier + synchronise; finally the ps tasks relaunch the kernel and announce it through the store."""
+        # (Kept short on purpose: NVLink sublinks drop into a low-power state after tens of milliseconds without
+        # traffic and the first pull after that costs ~200 us — measured, profiles/r2/nvlink_idle_probe.log — so the
+        # store polls below spin at 0.2 ms instead of sleeping 10 ms.)
         phase[0] += 1
         ph = phase[0]
+        t0 = time.perf_counter()
         if worker is not None:
             worker.wait_applied()
         if world > 1:
             if worker is not None:
                 rdv_any.add(f"bench/{ph}/quiet", 1)
             if ps_list:
-                rdv_any.wait_count(f"bench/{ph}/quiet", n_workers)
+                rdv_any.wait_count(f"bench/{ph}/quiet", n_workers, poll_s=0.0002)
         for ps in ps_list:
             ps.stop()
         barrier()
@@ -223,7 +232,8 @@ def main(argv=None) -> int:
             if world > 1:
                 if ps_list:
                     rdv_any.add(f"bench/{ph}/serving", 1)
-                rdv_any.wait_count(f"bench/{ph}/serving", args.num_ps)
+                rdv_any.wait_count(f"bench/{ph}/serving", args.num_ps, poll_s=0.0002)
+        sync_ms.append((time.perf_counter() - t0) * 1e3)
 
     n_rows = xrow = yrow = 0
     if worker is not None:
@@ -264,9 +274,9 @@ def main(argv=None) -> int:
     if worker is not None:
         resident_steps(W)
     sampler = ClockSampler(interval_ms=100, gpu_indices=list(range(n_gpus))) if rank == 0 else None
-    full_sync()
     if sampler:
-        sampler.start()
+        sampler.start()      # (before the synchronisation: spawning nvidia-smi takes tens of milliseconds)
+    full_sync()
 
     # ---------------- timed region 1: device-timed steps ----------------
     if worker is not None:
@@ -274,6 +284,11 @@ def main(argv=None) -> int:
         elapsed_ms, host_enqueue_ms = device_timed(K)
         launches = worker.kernel_launches() - launches_before + 1   # + the acknowledgement-wait kernel
     full_sync()
+    if os.environ.get("DM_FUSED_DEBUG_TS") == "1" and worker is not None and getattr(worker, "_fx_dbg", None) is not None:
+        from bench_tools.fused_phases import print_stamps   # in-kernel phase stamps of the timed launch (stderr)
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):
+            print_stamps(worker._fx_dbg.cpu(), f"rank {rank} lanes={args.lanes} K={K}")
 
     # ---------------- timed region 2: end to end through the public API ----------------
     if not args.skip_e2e:
@@ -307,6 +322,15 @@ def main(argv=None) -> int:
             worker.set_lanes(args.lanes, strict=args.strict_steps)
         full_sync()
 
+    if os.environ.get("DM_BENCH_PROBE") == "1" and worker is not None:
+        # diagnostic (stderr): cost of the first steps of a launch as a function of the idle time before it
+        for gap_ms in (0.0, 0.0, 0.2, 1.0, 5.0, 20.0, 100.0, 0.0):
+            if gap_ms:
+                time.sleep(gap_ms / 1e3)
+            ms20, _ = device_timed(20)
+            ms1, _ = device_timed(1)
+            print(f"[probe] rank {rank}: idle {gap_ms:6.1f} ms -> 20 steps in {ms20 * 1e3:8.1f} us, then 1 step in "
+                  f"{ms1 * 1e3:7.1f} us", file=sys.stderr, flush=True)
     final_step = worker.read_global_step() if (worker is not None and worker.is_chief) else 0
     full_sync(restart=False)   # serve kernels stay down from here on: torch/NCCL ops below are safe
     clocks = sampler.stop() if sampler is not None else None
@@ -378,6 +402,7 @@ def main(argv=None) -> int:
                 "l2_policy": "inputs stream from a 55000x784 device-resident dataset (172 MB fp32 > 126 MB L2); "
                              "parameters (0.3 MB) stay L2-resident as in real training",
                 "global_step_after_run": int(mx[5]),
+                "barrier_sync_ms": [round(v, 2) for v in sync_ms[:3]],
             },
             "clocks": clocks,
             "gpu_launches": int(sm[2]),

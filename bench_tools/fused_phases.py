@@ -11,7 +11,24 @@ from dist_mnist_b200.parallel.config import EngineConfig, OptimizerConfig
 from dist_mnist_b200.session import InProcessCluster
 from dist_mnist_b200.utils import data
 
-NAMES = ["start", "acc1", "rs_bar", "head", "ag_bar", "acc2", "pushed", "end"]
+NAMES = ["start", "acc1", "rs_bar", "head_in", "softmax", "grads_sent", "ag_bar", "acc2", "staged", "bar3",
+         "tile_published(w0)", "result(w0)"]
+KTS = 16
+
+
+def print_stamps(buf, tag):
+    """Epilogue thread 0 of cluster 0 / CTA 0 stamps 0..9, warp 0 (publisher) stamps 10, 11; first 4 steps."""
+    ts = buf.view(4, KTS)
+    t0 = int(ts[0, 0])
+    print(f"{tag}: cluster 0, SM cycles (1965 MHz -> /1965 = us); deltas to the previous stamp")
+    for j in range(4):
+        row = [int(ts[j, k]) - t0 for k in range(12)]
+        d = [row[k] - row[k - 1] if k else 0 for k in range(10)]
+        nxt = (int(ts[j + 1, 0]) - t0 - row[0]) if j + 1 < 4 else None
+        print(f"  step {j}: " + " ".join(f"{NAMES[k]}=+{d[k]}" for k in range(1, 10)) +
+              f" | publisher: tile at +{row[10] - row[9]} after bar3, result at +{row[11] - row[9]}"
+              f" | step {row[9] - row[0]} cyc = {(row[9] - row[0]) / 1965:.2f} us"
+              + (f", next step starts {nxt} cyc after this one" if nxt is not None else ""))
 
 
 def main():
@@ -29,14 +46,7 @@ def main():
             for rep in range(3):
                 w.run_resident(64, dev_x.data_ptr(), dev_y.data_ptr(), 784 * 4, 40, n_rows, rep * 64)
                 w.wait_applied()
-            ts = w._fx_dbg.cpu().view(8, 8)
-            t0 = int(ts[0, 0])
-            print(f"lanes={lanes}: cluster 0, cycles since its first step start (1965 MHz -> /1965 = us)")
-            for j in range(8):
-                row = [int(ts[j, k]) - t0 for k in range(8)]
-                d = [row[k] - row[k - 1] if k else 0 for k in range(8)]
-                print(f"  step {j}: " + " ".join(f"{NAMES[k]}=+{d[k]}" for k in range(1, 8)) +
-                      f"  | step total {row[7] - row[0]} cyc = {(row[7] - row[0]) / 1965:.2f} us; start at {row[0]}")
+            print_stamps(w._fx_dbg.cpu(), f"lanes={lanes}")
     return 0
 
 

@@ -149,7 +149,8 @@ class FusedParams(C.Structure):
 
 
 class FusedMaps(C.Structure):
-    _fields_ = [("w", (C.c_uint8 * 128) * FUSED_CLUSTER), ("xk", C.c_uint8 * 128), ("xmn", C.c_uint8 * 128)]
+    _fields_ = [("w", (C.c_uint8 * 128) * FUSED_CLUSTER), ("xk", C.c_uint8 * 128), ("xmn", C.c_uint8 * 128),
+                ("push", (C.c_uint8 * 128) * FUSED_CLUSTER)]
 
 
 _MIRRORS = {
@@ -201,6 +202,7 @@ def _declare(l: C.CDLL) -> None:
         "dm_stream_query": (i, [vp]),
         "dm_stream_wait_stream": (i, [vp, vp]),
         "dm_make_tensor_map_2d": (i, [vp, vp, i, u64, u64, u64, u32, u32, i]),
+        "dm_make_tensor_map_3d": (i, [vp, vp, u64, u64, u64, u64, u64, u32, u32]),
         "dm_gemm_smem_bytes": (i, [i, i, i]),
         "dm_launch_gemm": (i, [vp, vp, vp, i, i, i, i, vp]),
         "dm_launch_head": (i, [vp, vp]),
@@ -351,6 +353,17 @@ def ensure_prepared(device: int | None = None) -> None:
     if device not in _prepared_devices:
         check(lib().dm_prepare_kernels(device), "prepare kernels")
         _prepared_devices.add(device)
+
+
+def make_tensor_map_3d(ptr: int, dim0: int, dim1: int, dim2: int, stride1_bytes: int, stride2_bytes: int, box0: int,
+                       box1: int):
+    """3-D fp32 128-byte-swizzled tensor map [dim2][dim1][dim0], box {box0, box1, 1} (TMA-store destination)."""
+    if stride1_bytes % 16 != 0 or stride2_bytes % 16 != 0:
+        raise NativeError("TMA strides must be multiples of 16 bytes")
+    buf = (C.c_uint8 * TENSOR_MAP_BYTES)()
+    check(lib().dm_make_tensor_map_3d(C.addressof(buf), ptr, dim0, dim1, dim2, stride1_bytes, stride2_bytes, box0, box1),
+          "cuTensorMapEncodeTiled(3d)")
+    return buf
 
 
 def make_tensor_map(ptr: int, dtype: int, dim0: int, dim1: int, stride1_bytes: int, box0: int, box1: int,

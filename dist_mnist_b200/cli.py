@@ -41,7 +41,7 @@ DEFAULT_LANES = 8    # the engine's default (bench.py uses the same); --lanes 1 
 def engine_config_from_args(args, backend: str) -> EngineConfig:
     """The engine configuration every task derives from the command line (ps and worker tasks must agree)."""
     lanes = max(1, args.lanes)
-    nslots = args.nslots or 2 * lanes
+    nslots = args.nslots or max(4 * lanes, 8)
     gsteps = args.graph_steps or min(lanes, 4)
     return EngineConfig(backend=backend, dtype=args.dtype, nslots=nslots, apply_mode=args.apply_mode,
                         push_mode=args.push_mode, sharding=args.sharding, colocate=args.colocate, lanes=lanes,
@@ -77,7 +77,7 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--engine", choices=["auto", "fused", "graph"], default="auto",
                    help="fused: one persistent kernel runs whole steps (784-H-10, H <= 128, batch <= 32, fp32); "
                         "graph: per-layer kernels in a CUDA graph (any model / dtype)")
-    p.add_argument("--nslots", type=int, default=0, help="mailbox slots per worker (0 = 2 x lanes)")
+    p.add_argument("--nslots", type=int, default=0, help="mailbox slots per worker (0 = max(4 x lanes, 8))")
     p.add_argument("--lanes", type=int, default=DEFAULT_LANES,
                    help="steps of this worker in flight at once: bounded-staleness asynchronous SGD inside one worker "
                         "(1 = strictly one step after the other, like the reference's sess.run loop)")

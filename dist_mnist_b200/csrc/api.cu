@@ -210,6 +210,41 @@ int dm_make_tensor_map_2d(void* out, void* gptr, int dtype, uint64_t dim0, uint6
   return 0;
 }
 
+// 3-D fp32 tensor map [dim2][dim1][dim0] (dim0 contiguous), box {box0, box1, 1}, 128-byte swizzle: the mailbox slots
+// of one variable ([slot][row][col]) as the destination of the fused kernel's TMA-store gradient push.
+int dm_make_tensor_map_3d(void* out, void* gptr, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t stride1_bytes,
+                          uint64_t stride2_bytes, uint32_t box0, uint32_t box1) {
+  static PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+      g_err = "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed";
+      return -1;
+    }
+    encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  CUtensorMap tm;
+  cuuint64_t dims[3] = {dim0, dim1, dim2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, gptr, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled(3d) failed: CUresult %d (ptr=%p dims=%llu,%llu,%llu strides=%llu,%llu "
+             "box=%u,%u)", int(r), gptr, (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)dim2,
+             (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes, box0, box1);
+    g_err = buf;
+    return -1;
+  }
+  memcpy(out, &tm, sizeof(tm));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // kernel launches
 // ------------------------------------------------------------------------------------------

@@ -20,8 +20,14 @@
 //                    are reduce-scattered the same way (16 hidden units per CTA).
 //   dW + push        CTA r computes dW[:, its K-slice] = dpre^T (128 x 32) . x (32 x slice) with tcgen05.mma (x is
 //                    still in shared memory, MN-major view) and its epilogue *is the gradient push*: TMEM -> registers
-//                    -> st.global.v4 into this worker's mailbox slot in the ps shard's HBM (or red.add into the master
-//                    copy for async SGD), one cumulative st.release flag per tile.
+//                    -> swizzled staging tile in shared memory -> TMA store (cp.async.bulk.tensor, whole 128-byte
+//                    lines over NVLink) into this worker's mailbox slot in the ps shard's HBM — or a TMA *reduce-add*
+//                    into the master copy for async SGD (push == apply) — then one cumulative st.release flag per tile.
+//   publish          everything that waits for a round trip (store completion, the release of the tile flag, the small
+//                    variables' flags, the 16-byte step result into pinned host memory) is done by warp 0 *after* the
+//                    step's last cluster barrier, i.e. while the other warps already run the next step's forward.
+//   small variables  bias / W_last / b_last are pulled with cp.async.bulk on the same mbarrier as the W tiles: no
+//                    synchronous peer load is ever on the critical path.
 //
 // Steps are claimed dynamically (atomic counter), so `lanes` = gridDim.y clusters of one launch work on different
 // steps concurrently and a cluster that is scheduled late simply takes fewer steps. Within a cluster the next
@@ -60,10 +66,15 @@ constexpr uint32_t kOffScal = kOffDbl + 8 * kFsMaxC * 4;             // [8][2]  
 constexpr uint32_t kOffRedw = kOffScal + 8 * 2 * 4;                  // [8]         warp partials
 constexpr uint32_t kOffCtl = kOffRedw + 8 * 4;                       // next-step words [2]
 constexpr uint32_t kOffBar = kOffCtl + 32;                           // 4 mbarriers + TMEM slot
-constexpr uint32_t kFsSmemUsed = kOffBar + 64;
+constexpr uint32_t kOffRawWl = (kOffBar + 64 + 127) & ~127u;         // W_last as it sits in the arena [C][H] (bulk copy)
+constexpr uint32_t kOffRawB = kOffRawWl + (kFsPart - 1) * 128 * 4;   // hidden bias [H]
+constexpr uint32_t kOffRawBl = kOffRawB + 128 * 4;                   // b_last [C]
+constexpr uint32_t kOffStage = (kOffRawBl + 64 + 1023) & ~1023u;     // 4 x 16 KB  dW tile staging for the TMA store
+constexpr uint32_t kFsSmemUsed = kOffStage + kFusedMaxChunks * kFsWChunk;
 constexpr uint32_t kFsSmemBytes = kFsSmemUsed + 1024;                // + alignment slack
 static_assert(kOffA % 1024 == 0 && kOffXk % 1024 == 0 && kOffXmn % 1024 == 0, "swizzled tiles need 1024-byte alignment");
-static_assert(kOffBar % 8 == 0 && kOffRed % 16 == 0 && kOffSg % 16 == 0, "alignment");
+static_assert(kOffBar % 8 == 0 && kOffRed % 16 == 0 && kOffSg % 16 == 0 && kOffRawWl % 16 == 0 && kOffRawB % 16 == 0 &&
+              kOffRawBl % 16 == 0 && kOffStage % 1024 == 0, "alignment");
 static_assert(kFsSmemBytes <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -166,18 +177,27 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
   uint32_t cur = ctl_next[0];
 
   const bool dbg = p.debug_ts != nullptr && blockIdx.y == 0 && rank == 0;
+  const bool mailbox = p.shard[0].push.mode == PUSH_MAILBOX;
+  const int H = p.H, C = p.C, B = p.B;
+  const uint32_t wl_bytes = (static_cast<uint32_t>(C * H) * 4u + 15u) & ~15u;   // bulk copies move 16-byte multiples
+  const uint32_t b_bytes = (static_cast<uint32_t>(H) * 4u + 15u) & ~15u;        // (the arena pads every variable)
+  const uint32_t bl_bytes = (static_cast<uint32_t>(C) * 4u + 15u) & ~15u;
+  constexpr int kTs = 16;   // debug stamps per step
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
+    // =========================== TMA producer + publisher ===========================
     auto issue_wx = [&](uint32_t step) {
-      if (nkc == 0) { mbar_arrive(bar_w); return; }
       const int row0 = static_cast<int>(fs_row0(p, step));
-      mbar_arrive_expect_tx(bar_w, static_cast<uint32_t>(nkc) * (kFsWChunk + kFsXChunk));
+      mbar_arrive_expect_tx(bar_w, static_cast<uint32_t>(nkc) * (kFsWChunk + kFsXChunk) + wl_bytes + b_bytes + bl_bytes);
       for (int i = 0; i < nkc; ++i) {
         const int k0 = (sl.kc_begin + i) * 32;
         tma_load_2d(smem + kOffW + i * kFsWChunk, &maps.w[rank], bar_w, k0, 0);      // peer HBM -> smem (the pull)
         tma_load_2d(smem + kOffXk + i * kFsXChunk, &maps.xk, bar_w, k0, row0);
       }
+      // the small variables ride on the same barrier: no synchronous peer load anywhere in the step
+      bulk_load_1d(smem + kOffRawWl, p.w_last, wl_bytes, bar_w);
+      bulk_load_1d(smem + kOffRawB, p.bias_h, b_bytes, bar_w);
+      bulk_load_1d(smem + kOffRawBl, p.b_last, bl_bytes, bar_w);
     };
     auto issue_xmn = [&](uint32_t step) {
       if (nkc == 0) { mbar_arrive(bar_xmn); return; }
@@ -191,20 +211,122 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
       issue_xmn(cur);
     }
     __syncwarp();
+    const float* scal = reinterpret_cast<const float*>(smem + kOffScal);
+    // ---- publishing a finished step (lane 0): everything that costs memory round trips — an NVLink round trip when the
+    // ps is remote — and that nothing inside the step depends on
+    struct Pending { uint32_t step, seq; float loss, corr; uint32_t ts_slot; };
+    Pending pend{0u, 0u, 0.f, 0.f, 0u};
+    auto publish = [&](const Pending& d) {
+      const PushTarget& tw = p.shard[sl.shard].push;
+      const bool tile = nkc > 0;
+      if (tile) bulk_wait_group0();                       // my tile has reached the ps shard's memory
+      if (dbg && d.ts_slot < 4) p.debug_ts[d.ts_slot * kTs + 10] = clock64();
+      if (mailbox && (tile || rank == 0)) {
+        // one cumulative fence: my TMA-stored tile (async proxy) and — through cluster barrier #3 — every CTA's
+        // small-gradient stores are ordered before the flags below
+        fence_proxy_async();
+        fence_acq_rel_scoped(tw.gpu_scope);
+        if (tile) st_relaxed_sys_u32(fs_resolve(tw, d.seq).flags + sl.flag_index, d.seq);
+        if (rank == 0) {
+          st_relaxed_sys_u32(fs_resolve(p.shard[p.shard_wl].push, d.seq).flags + p.flag_wl, d.seq);
+          st_relaxed_sys_u32(fs_resolve(p.shard[p.shard_bh].push, d.seq).flags + p.flag_bh, d.seq);
+          st_relaxed_sys_u32(fs_resolve(p.shard[p.shard_bl].push, d.seq).flags + p.flag_bl, d.seq);
+        }
+      }
+      if (rank == 0) {
+        uint32_t gstep = d.seq;
+        if (mailbox) {
+          const volatile unsigned long long* ib = reinterpret_cast<const volatile unsigned long long*>(p.shard[0].inbox);
+          if (ib != nullptr) {
+            // {acked push, global_step} in one 8-byte load. global_step as of our last acknowledged push + our own
+            // pushes since then: exact with one worker, a lower bound under concurrency (the reference's fetched
+            // value is equally unordered w.r.t. peers)
+            const unsigned long long v = *ib;
+            gstep = static_cast<uint32_t>(v >> 32) + (d.seq - static_cast<uint32_t>(v));
+          }
+        } else if (p.shard[0].push.mode == PUSH_ATOMIC && p.ps_global_step != nullptr) {
+          gstep = atom_add_sys_u32(p.ps_global_step, 1u) + 1u;   // async SGD: this push *is* global step gstep
+        }
+        StepResult res;
+        res.loss = d.loss;
+        res.global_step = gstep;
+        res.correct = static_cast<uint32_t>(d.corr + 0.5f);
+        res.seq = d.seq;
+        p.results[d.step] = res;                              // pinned host memory: a 16-byte posted write
+        atomicAdd(p.seq_word, 1u);
+        if (p.stop_at != 0u && gstep >= p.stop_at) *reinterpret_cast<volatile uint32_t*>(p.stop_word) = 1u;
+        if (dbg && d.ts_slot < 4) p.debug_ts[d.ts_slot * kTs + 11] = clock64();
+      }
+    };
+    bool arrived1 = false;   // barrier #1 of the coming step already arrived at (early, see below)
+    bool deferred = false;   // `pend` holds a finished step whose publishing was deferred into this step's head phase
     for (uint32_t jl = 0; cur != kFusedNoStep; ++jl) {
-      cluster_sync_all();                                   // #1: forward accumulators are out of TMEM / smem
+      const uint32_t seq = p.seq_base + cur + 1u;
+      if (!arrived1) cluster_barrier_arrive_release();
+      cluster_barrier_wait_acquire();                       // #1: forward accumulators are out of TMEM / smem
       const uint32_t nxt = ctl_next[(jl + 1) & 1];
       if (lane == 0 && !p.strict && nxt != kFusedNoStep) issue_wx(nxt);   // W / x buffers are free: pull ahead
       __syncwarp();
-      cluster_sync_all();                                   // #2
-      cluster_sync_all();                                   // #3: dW MMAs of this step are complete
-      if (lane == 0 && nxt != kFusedNoStep) {
-        if (p.strict) {
-          // reference-exact read-your-writes: the next pull starts only after this step's push is applied
-          if (p.shard[0].push.mode == PUSH_MAILBOX) fs_wait_acks(p, p.seq_base + cur + 1u, "strict pull");
+      if (deferred) {
+        // EARLY ARRIVAL at barrier #2, then the previous step is published while the other warps run this step's
+        // head: nothing they do before their staging writes (which come after barrier #2) involves this warp.
+        cluster_barrier_arrive_release();                   // #2 (arrive)
+        if (lane == 0) publish(pend);
+        __syncwarp();
+        cluster_barrier_wait_acquire();                     // #2 (wait)
+        deferred = false;
+      } else {
+        cluster_sync_all();                                 // #2
+      }
+      // ---- the gradient push: the epilogue warps have staged the dW tile (swizzled, fence.proxy.async'ed) ----
+      named_bar_sync(2, 160);
+      {
+        const PushTarget& tw = p.shard[sl.shard].push;
+        const uint32_t slot = tw.mode == PUSH_MAILBOX ? seq % tw.nslots : 0u;
+        if (lane == 0 && nkc > 0) {
+          fence_proxy_async();
+          for (int i = 0; i < nkc; ++i) {
+            const void* src = smem + kOffStage + i * kFsWChunk;
+            const int c0 = (sl.kc_begin + i) * 32;
+            if (tw.mode == PUSH_ATOMIC) tma_reduce_add_3d(&maps.push[rank], src, c0, 0, 0);   // push == apply (SGD)
+            else tma_store_3d(&maps.push[rank], src, c0, 0, static_cast<int>(slot));          // rows >= H / cols >= I clipped
+          }
+          bulk_commit_group();
+        }
+      }
+      __syncwarp();
+      cluster_sync_all();                                   // #3: dW MMAs done, every CTA's small-gradient stores issued
+      // What the publisher needs of this step is read now: once this warp has arrived at the next step's barriers the
+      // other warps run ahead and overwrite the per-step shared-memory state.
+      pend.step = cur;
+      pend.seq = seq;
+      pend.ts_slot = jl;
+      pend.loss = pend.corr = 0.f;
+      if (rank == 0 && lane == 0) {
+#pragma unroll
+        for (int src = 0; src < kFusedCluster; ++src) { pend.loss += scal[src * 2]; pend.corr += scal[src * 2 + 1]; }
+      }
+      if (lane == 0 && nxt != kFusedNoStep) issue_xmn(nxt);  // (the dW MMAs that read the MN-major x tile are complete)
+      // Publishing costs several memory round trips (an NVLink round trip when the ps is remote): store completion,
+      // a system-scope fence, the flags, the step result. It is deferred into the next step's head phase (see above)
+      // unless (a) strict mode wants the acknowledgement before the next pull, (b) this was the cluster's last step,
+      // or (c) the next step's mailbox flow control could wait for an acknowledgement that depends on these very
+      // flags: the ps acknowledges in push order, the next step waits for push (next_seq - nslots), and that is at or
+      // beyond this push only if the two claims are >= nslots apart — publish first whenever they are >= nslots / 2.
+      deferred = !p.strict && nxt != kFusedNoStep && (nxt - cur) < (p.nslots >> 1);
+      if (deferred && lane == 0 && nkc > 0) bulk_wait_group_read0();   // staging tile read: the next step may refill it
+      __syncwarp();
+      // EARLY ARRIVAL at barrier #1 of the next step: the other warps' next forward / reduce-scatter never waits for
+      // this warp; it only *waits* for that barrier when it gets back to the loop top.
+      arrived1 = nxt != kFusedNoStep;
+      if (arrived1) cluster_barrier_arrive_release();
+      if (!deferred && lane == 0) {
+        publish(pend);
+        if (nxt != kFusedNoStep && p.strict) {
+          // strict: reference-exact read-your-writes — the next pull starts only after this step's push is applied
+          if (mailbox) fs_wait_acks(p, seq, "strict pull");
           issue_wx(nxt);
         }
-        issue_xmn(nxt);
       }
       __syncwarp();
       cur = nxt;
@@ -256,7 +378,6 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
     const int q = warp & 3;                       // TMEM lane quarter of this warp
     const int et = q * 32 + lane;                 // TMEM lane == hidden unit == tile row
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const int B = p.B, H = p.H, C = p.C;
     const bool unit_ok = et < H;
     float* red = reinterpret_cast<float*>(smem + kOffRed);
     float* sg = reinterpret_cast<float*>(smem + kOffSg);
@@ -264,36 +385,35 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
     float* wls = reinterpret_cast<float*>(smem + kOffWl);
     float* dls = reinterpret_cast<float*>(smem + kOffDl);
     float* dbl = reinterpret_cast<float*>(smem + kOffDbl);
-    float* scal = reinterpret_cast<float*>(smem + kOffScal);
     float* redw = reinterpret_cast<float*>(smem + kOffRedw);
-    const bool mailbox = p.shard[0].push.mode == PUSH_MAILBOX;
-    const uint32_t scope = p.shard[0].push.gpu_scope;
+    const float* raw_wl = reinterpret_cast<const float*>(smem + kOffRawWl);
+    const float* raw_b = reinterpret_cast<const float*>(smem + kOffRawB);
+    const float* raw_bl = reinterpret_cast<const float*>(smem + kOffRawBl);
+    // head role of this thread: warp q handles batch row q of this CTA; lane -> (class hc, k-half kh)
+    const int hc = lane >> 1, kh = lane & 1;
+    const bool hc_ok = hc < C;
+    const int brow = static_cast<int>(rank) * kFsRows + q;
+    const bool hrow_ok = brow < B;
 
     for (uint32_t jl = 0; cur != kFusedNoStep; ++jl) {
       const uint32_t seq = p.seq_base + cur + 1u;
-      if (dbg && et == 0 && jl < 8) p.debug_ts[jl * 8 + 0] = clock64();
-      // ---- step prologue: everything that does not depend on the forward result is requested now ----
+      if (dbg && et == 0 && jl < 4) p.debug_ts[jl * kTs + 0] = clock64();
+      // ---- step prologue ----
       if (is_claimer) broadcast_next((jl + 1) & 1, claim());
-      const float bias = unit_ok ? p.bias_h[et] : 0.f;          // peer loads from the ps shard(s)
-      float wl[kFsMaxC];
-#pragma unroll
-      for (int c = 0; c < kFsMaxC; ++c) wl[c] = (unit_ok && c < C) ? p.w_last[static_cast<size_t>(c) * H + et] : 0.f;
-      // head role of this thread (threads et < 64): (row rr, class hc)
-      const int rr = (et >> 4) & 3, hc = et & 15;
-      const int brow = static_cast<int>(rank) * kFsRows + rr;
-      const bool hrow_ok = et < 64 && brow < B;
-      const bool hc_ok = hc < C;
-      float ylab = 0.f, blast = 0.f;
-      if (et < 64) {
-        if (hrow_ok && hc_ok) ylab = p.y_base[(fs_row0(p, cur) + static_cast<uint64_t>(brow)) * C + hc];
-        if (hc_ok) blast = p.b_last[hc];
-      }
+      float ylab = 0.f;
+      if (hrow_ok && hc_ok) ylab = p.y_base[(fs_row0(p, cur) + static_cast<uint64_t>(brow)) * C + hc];
       if (et == 127 && mailbox && seq > p.nslots) fs_wait_acks(p, seq - p.nslots, "flow control");
 
       // ---- forward partial -> reduce-scatter over the cluster ----
-      mbar_wait(bar_acc1, jl & 1);
+      mbar_wait(bar_acc1, jl & 1);   // (implies this step's W / x / small variables have landed: the MMAs waited for them)
       tcgen05_fence_after();
-      if (dbg && et == 0 && jl < 8) p.debug_ts[jl * 8 + 1] = clock64();
+      if (dbg && et == 0 && jl < 4) p.debug_ts[jl * kTs + 1] = clock64();
+      // small variables out of the bulk-copied image, before barrier #1 lets warp 0 overwrite it with the next pull
+      const float bias = unit_ok ? raw_b[et] : 0.f;
+      float wl[kFsMaxC];
+#pragma unroll
+      for (int c = 0; c < kFsMaxC; ++c) wl[c] = (unit_ok && c < C) ? raw_wl[c * H + et] : 0.f;
+      const float blast = hc_ok ? raw_bl[hc] : 0.f;
       {
         uint32_t r[32];
         if (nkc > 0) {
@@ -312,7 +432,7 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
       }
       tcgen05_fence_before();
       cluster_sync_all();                                   // #1
-      if (dbg && et == 0 && jl < 8) p.debug_ts[jl * 8 + 2] = clock64();
+      if (dbg && et == 0 && jl < 4) p.debug_ts[jl * kTs + 2] = clock64();
       float hv[kFsRows];
       {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -332,22 +452,26 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
 #pragma unroll
       for (int c = 0; c < kFsMaxC; ++c) wls[c * kFsWlStride + et] = wl[c];
       named_bar_sync(1, 128);
-      if (et < 64) {   // warps with q == 0, 1 (warp-uniform)
+      if (dbg && et == 0 && jl < 4) p.debug_ts[jl * kTs + 3] = clock64();
+      {
+        // logits: warp q = row q of this CTA, lane = (class, half of the hidden units)
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        const float* hrow = val + rr * 128;
-        const float* wrow = wls + hc * kFsWlStride;
-#pragma unroll 8
-        for (int k = 0; k < 128; k += 4) {   // units >= H are zero in both operands
+        const float* hrow = val + q * 128 + kh * 64;
+        const float* wrow = wls + hc * kFsWlStride + kh * 64;
+#pragma unroll
+        for (int k = 0; k < 64; k += 4) {   // units >= H are zero in both operands
           const float4 hvv = *reinterpret_cast<const float4*>(hrow + k);
           const float4 wv = *reinterpret_cast<const float4*>(wrow + k);
           a0 = fmaf(hvv.x, wv.x, a0); a1 = fmaf(hvv.y, wv.y, a1);
           a2 = fmaf(hvv.z, wv.z, a2); a3 = fmaf(hvv.w, wv.w, a3);
         }
+        float dot = (a0 + a1) + (a2 + a3);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
         const float y = ylab;
-        const float z = hc_ok ? (a0 + a1) + (a2 + a3) + blast : -INFINITY;
+        const float z = hc_ok ? dot + blast : -INFINITY;
         float zmax = z, ybest = hc_ok ? y : -INFINITY, ysum = y;
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
+        for (int o = 16; o > 1; o >>= 1) {   // over the 16 classes (lane bit 0 is the k-half: both halves hold the same)
           zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
           ybest = fmaxf(ybest, __shfl_xor_sync(0xffffffffu, ybest, o));
           ysum += __shfl_xor_sync(0xffffffffu, ysum, o);
@@ -356,12 +480,12 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
         const float e = hc_ok ? __expf(z - zmax) : 0.f;
         float esum = e;
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
+        for (int o = 16; o > 1; o >>= 1) {
           zarg = min(zarg, __shfl_xor_sync(0xffffffffu, zarg, o));
           yarg = min(yarg, __shfl_xor_sync(0xffffffffu, yarg, o));
           esum += __shfl_xor_sync(0xffffffffu, esum, o);
         }
-        const float pc = e / esum;
+        const float pc = __fdividef(e, esum);
         float dl = 0.f, lc = 0.f;
         if (p.loss_kind == LOSS_BOOK) {
           // L = -(1/(B*C)) sum y*log(clip(p,1e-10,1));  dL/dp = -y/(B*C*p) where the clip passes gradient (DS:52-53)
@@ -370,7 +494,7 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
           const float g = pass ? (-k * y / pc) : 0.f;
           float gp = g * pc;
 #pragma unroll
-          for (int o = 8; o > 0; o >>= 1) gp += __shfl_xor_sync(0xffffffffu, gp, o);
+          for (int o = 16; o > 1; o >>= 1) gp += __shfl_xor_sync(0xffffffffu, gp, o);
           dl = pc * (g - gp);
           lc = hc_ok ? -k * y * __logf(fminf(fmaxf(pc, 1e-10f), 1.0f)) : 0.f;
         } else {
@@ -379,17 +503,16 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
           dl = k * (pc * ysum - y);
           lc = hc_ok ? -k * y * (z - (zmax + __logf(esum))) : 0.f;
         }
-        dls[rr * kFsMaxC + hc] = (hrow_ok && hc_ok) ? dl : 0.f;
-        float loss_part = hrow_ok ? lc : 0.f;
-        float corr_part = (hrow_ok && hc == 0 && zarg == yarg) ? 1.f : 0.f;
+        if (kh == 0) dls[q * kFsMaxC + hc] = (hrow_ok && hc_ok) ? dl : 0.f;
+        float loss_part = (hrow_ok && kh == 0) ? lc : 0.f;
+        float corr_part = (hrow_ok && lane == 0 && zarg == yarg) ? 1.f : 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          loss_part += __shfl_xor_sync(0xffffffffu, loss_part, o);
-          corr_part += __shfl_xor_sync(0xffffffffu, corr_part, o);
-        }
+        for (int o = 16; o > 0; o >>= 1) loss_part += __shfl_xor_sync(0xffffffffu, loss_part, o);
+        corr_part = __shfl_sync(0xffffffffu, corr_part, 0);
         if (lane == 0) { redw[q] = loss_part; redw[4 + q] = corr_part; }
       }
       named_bar_sync(1, 128);
+      if (dbg && et == 0 && jl < 4) p.debug_ts[jl * kTs + 4] = clock64();
       // ---- gradients of my rows; thread -> hidden unit et ----
       float dw[kFsPart];
 #pragma unroll
@@ -433,20 +556,21 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
           st_shared_cluster_f32(mapa_shared_cluster(sbase + kOffDbl + (rank * kFsMaxC + et) * 4u, 0), sdl);
         }
         if (et == 0) {
-          st_shared_cluster_f32(mapa_shared_cluster(sbase + kOffScal + (rank * 2u) * 4u, 0), redw[0] + redw[1]);
-          st_shared_cluster_f32(mapa_shared_cluster(sbase + kOffScal + (rank * 2u + 1u) * 4u, 0), redw[4] + redw[5]);
+          st_shared_cluster_f32(mapa_shared_cluster(sbase + kOffScal + (rank * 2u) * 4u, 0),
+                                (redw[0] + redw[1]) + (redw[2] + redw[3]));
+          st_shared_cluster_f32(mapa_shared_cluster(sbase + kOffScal + (rank * 2u + 1u) * 4u, 0),
+                                (redw[4] + redw[5]) + (redw[6] + redw[7]));
         }
       }
       fence_proxy_async();
-      if (dbg && et == 0 && jl < 8) p.debug_ts[jl * 8 + 3] = clock64();
+      if (dbg && et == 0 && jl < 4) p.debug_ts[jl * kTs + 5] = clock64();
       cluster_sync_all();                                   // #2
-      if (dbg && et == 0 && jl < 8) p.debug_ts[jl * 8 + 4] = clock64();
+      if (dbg && et == 0 && jl < 4) p.debug_ts[jl * kTs + 6] = clock64();
 
       // ---- small gradients: sum the 8 sources for my 16 hidden units and push them ----
-      const FsPush pw_l = fs_resolve(p.shard[p.shard_wl].push, seq);
-      const FsPush pb_h = fs_resolve(p.shard[p.shard_bh].push, seq);
-      const FsPush pb_l = fs_resolve(p.shard[p.shard_bl].push, seq);
       {
+        const FsPush pw_l = fs_resolve(p.shard[p.shard_wl].push, seq);
+        const FsPush pb_h = fs_resolve(p.shard[p.shard_bh].push, seq);
         const int u = et & 15, vg = et >> 4;   // values vg (0..7) and vg + 8 (8..11) of unit u
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
@@ -461,31 +585,24 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
             fs_push_value(p.shard[p.shard_wl].push, pw_l.base + p.off_wl + static_cast<size_t>(vg + 8) * H + unit, s1);
           if (vg == 3) fs_push_value(p.shard[p.shard_bh].push, pb_h.base + p.off_bh + unit, s1);
         }
-      }
-      float loss_tot = 0.f, corr_tot = 0.f;
-      if (rank == 0) {
-        if (et < C) {
+        if (rank == 0 && et < C) {
+          const FsPush pb_l = fs_resolve(p.shard[p.shard_bl].push, seq);
           float s = 0.f;
 #pragma unroll
           for (int src = 0; src < kFusedCluster; ++src) s += dbl[src * kFsMaxC + et];
           fs_push_value(p.shard[p.shard_bl].push, pb_l.base + p.off_bl + et, s);
         }
-        if (et == 0) {
-#pragma unroll
-          for (int src = 0; src < kFusedCluster; ++src) { loss_tot += scal[src * 2]; corr_tot += scal[src * 2 + 1]; }
-        }
       }
 
-      // ---- dW tile of my K-slice: the epilogue is the gradient push ----
+      // ---- dW tile of my K-slice: TMEM -> registers -> swizzled staging tile; warp 0 TMA-stores it (the push) ----
       mbar_wait(bar_acc2, jl & 1);
       tcgen05_fence_after();
-      if (dbg && et == 0 && jl < 8) p.debug_ts[jl * 8 + 5] = clock64();
-      const PushTarget& tw = p.shard[sl.shard].push;
-      const FsPush pw = fs_resolve(tw, seq);
+      if (dbg && et == 0 && jl < 4) p.debug_ts[jl * kTs + 7] = clock64();
       if (nkc > 0) {
-        float* row = pw.base + sl.w_offset + static_cast<size_t>(et) * p.ldw + static_cast<size_t>(sl.kc_begin) * 32;
-        const int col0 = sl.kc_begin * 32;
-        const float sc = tw.scale;
+        const PushTarget& tw = p.shard[sl.shard].push;
+        const float sc = tw.mode == PUSH_ATOMIC ? tw.scale : 1.f;
+        uint8_t* stage_row = smem + kOffStage + static_cast<uint32_t>(et) * 128u;
+        const uint32_t sw = static_cast<uint32_t>(et) & 7u;
         uint32_t ra[32], rb[32];
         tmem_ld_32x32b_x32_nowait(taddr + kFsAcc2Col, ra);
 #pragma unroll
@@ -495,55 +612,19 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
           uint32_t (&cur_r)[32] = (i & 1) ? rb : ra;
           uint32_t (&nxt_r)[32] = (i & 1) ? ra : rb;
           if (i + 1 < nkc) tmem_ld_32x32b_x32_nowait(taddr + kFsAcc2Col + 32u * (i + 1), nxt_r);   // overlaps the stores
-          if (unit_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const int c = col0 + i * 32 + j;
-              if (c < p.I) {   // I is a multiple of 4 (checked on the host): whole 16-byte groups
-                float* dst = row + i * 32 + j;
-                const float v0 = __uint_as_float(cur_r[j]), v1 = __uint_as_float(cur_r[j + 1]);
-                const float v2 = __uint_as_float(cur_r[j + 2]), v3 = __uint_as_float(cur_r[j + 3]);
-                if (tw.mode == PUSH_ATOMIC) red_add_sys_v4f32(dst, sc * v0, sc * v1, sc * v2, sc * v3);
-                else st_global_v4f32(dst, v0, v1, v2, v3);
-              }
-            }
-          }
+          for (uint32_t j = 0; j < 8; ++j)   // 16-byte piece j of this row -> position j ^ (row & 7) (SWIZZLE_128B)
+            *reinterpret_cast<float4*>(stage_row + i * kFsWChunk + ((j ^ sw) << 4)) =
+                make_float4(sc * __uint_as_float(cur_r[4 * j]), sc * __uint_as_float(cur_r[4 * j + 1]),
+                            sc * __uint_as_float(cur_r[4 * j + 2]), sc * __uint_as_float(cur_r[4 * j + 3]));
         }
       }
+      fence_proxy_async();             // staging writes -> visible to the TMA engine
       tcgen05_fence_before();
-      // Publish: the barrier orders every lane's P2P stores before the single cumulative release of the tile flag.
-      named_bar_sync(1, 128);
-      if (mailbox && et == 0 && nkc > 0) st_release_scoped_u32(pw.flags + sl.flag_index, seq, tw.gpu_scope);
-      if (dbg && et == 0 && jl < 8) p.debug_ts[jl * 8 + 6] = clock64();
-      cluster_sync_all();                                   // #3: every CTA's small-gradient stores are ordered before
-      if (rank == 0 && et == 0) {                           //     the flags CTA 0 publishes now
-        uint32_t gstep = seq;
-        if (mailbox) {
-          fence_acq_rel_scoped(scope);
-          st_relaxed_sys_u32(pw_l.flags + p.flag_wl, seq);
-          st_relaxed_sys_u32(pb_h.flags + p.flag_bh, seq);
-          st_relaxed_sys_u32(pb_l.flags + p.flag_bl, seq);
-          const volatile uint32_t* ib = reinterpret_cast<const volatile uint32_t*>(p.shard[0].inbox);
-          if (ib != nullptr) {
-            // global_step as of our last acknowledged push + our own pushes since then: exact with one worker,
-            // a lower bound under concurrency (the reference's fetched value is equally unordered w.r.t. peers)
-            const uint32_t ack = ib[0];
-            __threadfence();
-            gstep = ib[1] + (seq - ack);
-          }
-        } else if (p.shard[0].push.mode == PUSH_ATOMIC && p.ps_global_step != nullptr) {
-          gstep = atom_add_sys_u32(p.ps_global_step, 1u) + 1u;   // async SGD: this push *is* global step gstep
-        }
-        StepResult res;
-        res.loss = loss_tot;
-        res.global_step = gstep;
-        res.correct = static_cast<uint32_t>(corr_tot + 0.5f);
-        res.seq = seq;
-        p.results[cur] = res;                               // pinned host memory: a 16-byte posted write
-        atomicAdd(p.seq_word, 1u);
-        if (p.stop_at != 0u && gstep >= p.stop_at) *reinterpret_cast<volatile uint32_t*>(p.stop_word) = 1u;
-        if (dbg && jl < 8) p.debug_ts[jl * 8 + 7] = clock64();
-      }
+      named_bar_arrive(2, 160);        // hand the tile to warp 0 (non-blocking) ...
+      if (dbg && et == 0 && jl < 4) p.debug_ts[jl * kTs + 8] = clock64();
+      cluster_sync_all();              // #3 ... and go on to the next step
+      if (dbg && et == 0 && jl < 4) p.debug_ts[jl * kTs + 9] = clock64();
       cur = ctl_next[(jl + 1) & 1];
     }
   }

@@ -577,6 +577,16 @@ class Worker:
             seg = self.ps_segs[sl.ps]
             tm = N.make_tensor_map(seg.addr("params", sl.w_offset * 4), N.DT_F32, I, vl.rows, vl.ld * 4, 32, 128)
             C.memmove(C.addressof(m.w[sl.rank]), C.addressof(tm), N.TENSOR_MAP_BYTES)
+            # destination of this CTA's TMA-store push: [slot][H][I] view of our mailbox for the hidden weight on that
+            # shard (mailbox mode), or of the master copy itself (atomic mode: TMA reduce-add, push == apply)
+            desc = self.ps_desc[sl.ps]
+            arena, ns = desc["arena_elems"], self.cfg.nslots
+            if self.cfg.push_mode == "atomic":
+                tp = N.make_tensor_map_3d(seg.addr("params", sl.w_offset * 4), I, vl.rows, 1, vl.ld * 4, arena * 4, 32, 128)
+            else:
+                base = seg.addr("mailbox", (self.task_index * ns * arena + sl.w_offset) * 4)
+                tp = N.make_tensor_map_3d(base, I, vl.rows, ns, vl.ld * 4, arena * 4, 32, 128)
+            C.memmove(C.addressof(m.push[sl.rank]), C.addressof(tp), N.TENSOR_MAP_BYTES)
         xk = N.make_tensor_map(x_ptr, N.DT_F32, I, n_rows, I * 4, 32, 32)
         xmn = N.make_tensor_map(x_ptr, N.DT_F32, I, n_rows, I * 4, 32, 32, mn_major=True)
         C.memmove(C.addressof(m.xk), C.addressof(xk), N.TENSOR_MAP_BYTES)

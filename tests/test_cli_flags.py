@@ -59,7 +59,7 @@ def test_engine_flags_defaults_are_the_benchmarked_engine_and_lanes_1_is_the_ref
     cfg.validate(OptimizerConfig("adam", 1e-4))
     a = cli.build_parser().parse_args(["--lanes", "1", "--strict_steps"])
     cfg = cli.engine_config_from_args(a, "cpu")
-    assert (cfg.lanes, cfg.nslots, cfg.graph_steps, cfg.strict_steps) == (1, 2, 1, True)
+    assert (cfg.lanes, cfg.nslots, cfg.graph_steps, cfg.strict_steps) == (1, 8, 1, True)
     cfg.validate(OptimizerConfig("adam", 1e-4))
     a = cli.build_parser().parse_args(["--lanes", "4", "--graph_steps=2", "--nslots", "4"])
     cfg = cli.engine_config_from_args(a, "cpu")
