@@ -94,6 +94,12 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
       : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Restricted to shared memory: orders this thread's shared-memory writes (own CTA / whole cluster) against later
+// async-proxy accesses without waiting for its outstanding *global* (possibly NVLink peer) stores.
+__device__ __forceinline__ void fence_proxy_async_smem_cta() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem_cluster() {
+  asm volatile("fence.proxy.async.shared::cluster;" ::: "memory");
+}
 // TMA store (shared -> global, possibly NVLink peer memory): 3-D tile {c0, c1, c2} of the tensor map, bulk-group
 // completion. The reduce variant adds (fp32) instead of overwriting: push == apply for asynchronous SGD.
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1, int c2) {

@@ -284,7 +284,7 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
         const PushTarget& tw = p.shard[sl.shard].push;
         const uint32_t slot = tw.mode == PUSH_MAILBOX ? seq % tw.nslots : 0u;
         if (lane == 0 && nkc > 0) {
-          fence_proxy_async();
+          fence_proxy_async_smem_cta();
           for (int i = 0; i < nkc; ++i) {
             const void* src = smem + kOffStage + i * kFsWChunk;
             const int c0 = (sl.kc_begin + i) * 32;
@@ -354,7 +354,7 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
       tcgen05_fence_before();
       cluster_sync_all();                                   // #2: dpre^T (A operand) is complete in my smem
       tcgen05_fence_after();
-      fence_proxy_async();                                  // generic-proxy (DSMEM) writes -> tensor-core reads
+      fence_proxy_async_smem_cta();                         // generic-proxy (DSMEM) writes -> tensor-core reads
       mbar_wait(bar_xmn, jl & 1);
       tcgen05_fence_after();
       if (lane == 0) {
@@ -562,7 +562,7 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
                                 (redw[4] + redw[5]) + (redw[6] + redw[7]));
         }
       }
-      fence_proxy_async();
+      fence_proxy_async_smem_cluster();
       if (dbg && et == 0 && jl < 4) p.debug_ts[jl * kTs + 5] = clock64();
       cluster_sync_all();                                   // #2
       if (dbg && et == 0 && jl < 4) p.debug_ts[jl * kTs + 6] = clock64();
@@ -619,7 +619,8 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
                             sc * __uint_as_float(cur_r[4 * j + 2]), sc * __uint_as_float(cur_r[4 * j + 3]));
         }
       }
-      fence_proxy_async();             // staging writes -> visible to the TMA engine
+      fence_proxy_async_smem_cta();    // staging writes -> visible to the TMA engine (shared memory only: does not
+                                       // wait for the small-gradient peer stores issued above)
       tcgen05_fence_before();
       named_bar_arrive(2, 160);        // hand the tile to warp 0 (non-blocking) ...
       if (dbg && et == 0 && jl < 4) p.debug_ts[jl * kTs + 8] = clock64();
