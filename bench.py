@@ -271,11 +271,16 @@ def main(argv=None) -> int:
     par = {"dev_ms": 0.0, "e2e_s": 0.0, "strict_ms": 0.0}
     h2d_bytes = d2h_bytes = 0
     launches = 0
-    if worker is not None:
-        resident_steps(W)
+    # clocks are sampled from here to the end of the last timed region (started before the warm-up: nvidia-smi's own
+    # start-up takes tens of milliseconds and contends for driver locks, which must not sit between the barrier and
+    # the first timed launch)
     sampler = ClockSampler(interval_ms=100, gpu_indices=list(range(n_gpus))) if rank == 0 else None
     if sampler:
-        sampler.start()      # (before the synchronisation: spawning nvidia-smi takes tens of milliseconds)
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    if worker is not None:
+        resident_steps(W)
     full_sync()
 
     # ---------------- timed region 1: device-timed steps ----------------
