@@ -55,7 +55,7 @@ class EngineConfig:
                                      # clusters under profilers / sanitizers; `smoke()`)
     ps_ctas: int = 0                 # CTAs of the persistent PS kernel (0 = auto: 120 on a dedicated ps GPU,
                                      # 32 when a worker shares the GPU)
-    pipeline_slots: int = 4          # worker executor ring depth
+    pipeline_slots: int = 0          # graph engine: worker executor ring depth (0 = auto: max(4, 2 x lanes))
     lanes: int = 1                   # steps of one worker in flight on the GPU at once. 1 = each step starts after
                                      # the previous one's kernels (reference-like); n = step i+1's pull/forward
                                      # overlaps step i's backward/push (asynchronous SGD; needs nslots >= lanes)
@@ -109,11 +109,16 @@ class EngineConfig:
             raise ValueError("lanes must be a positive multiple of graph_steps")
         if self.push_mode == "mailbox" and self.lanes > self.nslots:
             raise ValueError("lanes (steps in flight) cannot exceed nslots (mailbox slots per worker)")
-        if not (self.lanes <= self.pipeline_slots <= MAX_SLOTS) or self.pipeline_slots % u != 0 \
-                or (self.pipeline_slots // u) % (self.lanes // u) != 0:
+        ring = self.ring_slots
+        if not (self.lanes <= ring <= MAX_SLOTS) or ring % u != 0 or (ring // u) % (self.lanes // u) != 0:
             raise ValueError(f"pipeline_slots must be <= {MAX_SLOTS}, a multiple of graph_steps, and hold a whole "
                              "number of rounds of lanes")
         _ = self.native_dtype, self.native_apply_mode, opt.native_kind
+
+    @property
+    def ring_slots(self) -> int:
+        """Executor ring depth of the graph engine: `pipeline_slots`, or two rounds of lanes when left at 0."""
+        return self.pipeline_slots or max(4, 2 * self.lanes)
 
     def as_dict(self) -> dict:
         return asdict(self)

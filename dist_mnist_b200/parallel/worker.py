@@ -425,7 +425,7 @@ class Worker:
         x_bytes = self.B_pad * self.ld_in * self.es
         y_bytes = self.B_pad * spec.num_classes * 4
         out = C.c_void_p()
-        N.check(self.lib.dm_exec_create(self.device, cfg.pipeline_slots, cfg.lanes, cfg.graph_steps, x_bytes, y_bytes,
+        N.check(self.lib.dm_exec_create(self.device, cfg.ring_slots, cfg.lanes, cfg.graph_steps, x_bytes, y_bytes,
                                         C.byref(out)), "exec create")
         self._exec = out.value
         self.x_bytes, self.y_bytes = x_bytes, y_bytes
@@ -436,7 +436,7 @@ class Worker:
         # activations / pre-activation gradients of the hidden layers (row padded, zero initialised)
         # (one set per executor slot: steps of different slots may run concurrently)
         self._slot_act = [[None] + [torch.zeros(self.B_pad, gemm_ops.padded_ld(sizes[l][1]), dtype=self.tdtype,
-                                                device=dev) for l in range(L - 1)] for _ in range(cfg.pipeline_slots)]
+                                                device=dev) for l in range(L - 1)] for _ in range(cfg.ring_slots)]
         self._slot_dact = [[None] + [torch.zeros_like(a[l + 1]) for l in range(L - 1)] for a in self._slot_act]
         self.act, self.dact = self._slot_act[0], self._slot_dact[0]
         seq_counter = self.seg.addr("seq")
@@ -464,7 +464,7 @@ class Worker:
             num_classes=spec.num_classes, loss_kind=N.LOSS_BOOK if spec.loss == "book" else N.LOSS_XENT,
             act_bf16=cfg.dtype == "bf16", compute_grads=False, ldh=self.act[L - 1].shape[1]))
         torch.cuda.synchronize(self.device)
-        for slot in range(cfg.pipeline_slots):
+        for slot in range(cfg.ring_slots):
             act, dact = self._slot_act[slot], self._slot_dact[slot]
             seq_ptr = self.seg.addr("seq", 4 * (1 + slot))
             stream = self.lib.dm_exec_capture_stream(self._exec, slot)
@@ -552,7 +552,7 @@ class Worker:
         # group graphs: the U steps of a group as parallel chains of one graph (native loops launch these)
         U = cfg.graph_steps
         if U > 1:
-            for g in range(cfg.pipeline_slots // U):
+            for g in range(cfg.ring_slots // U):
                 N.check(self.lib.dm_exec_begin_group_capture(self._exec, g), "begin group capture")
                 try:
                     for u in range(U):

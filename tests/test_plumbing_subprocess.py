@@ -133,3 +133,58 @@ def test_crashed_worker_can_be_restarted_and_rejoins():
     # the restarted worker really trained: it reported steps of its own
     assert "INFO global_step/sec" in out1b, out1b
     assert "Train step 2500, loss:" in (out0 + out1b) or "Train step 2000, loss:" in (out0 + out1b)
+
+
+@pytest.mark.timeout(300)
+def test_restarted_chief_does_not_reinitialize_live_variables():
+    """Round-1 advisor finding: a restarted chief (worker 0) used to run the initialisers again on the live ps shards
+    (parameters and Adam slots reset while global_step and the per-item step counts kept running, loss jumped from
+    ~4e-5 to 0.08). It must see that the variables are live and simply rejoin."""
+    ps_hosts = f"127.0.0.1:{_free_port()}"
+    worker_hosts = f"127.0.0.1:{_free_port()},127.0.0.1:{_free_port()}"
+    common = ["--train_steps", "4000", "--learning_rate", "0.001", "--log_every", "100", "--chunk_sleep", "0.1"]
+    ps = _spawn("ps", 0, ps_hosts, worker_hosts, common + ["--ps_exit_when_done"])
+    w0 = _spawn("worker", 0, ps_hosts, worker_hosts, common + ["--inject_fault", "200"])
+    w1 = _spawn("worker", 1, ps_hosts, worker_hosts, common)
+    out0 = _finish(w0, 120)
+    assert w0.returncode == 42, out0
+    w0b = _spawn("worker", 0, ps_hosts, worker_hosts, common + ["--metrics_file", os.devnull, "--log_steps_per_sec"])
+    out0b = _finish(w0b, 240)
+    out1 = _finish(w1, 240)
+    outp = _finish(ps, 60)
+    assert w0b.returncode == 0, out0b
+    assert w1.returncode == 0, out1
+    assert ps.returncode == 0, outp
+    assert "variables are live on the ps, not re-initialising" in out0b, out0b
+    # training continued from the live state: whatever the restarted chief logged is far below the fresh-init loss
+    # (~0.23) — after a re-initialisation its first logged losses would be back up there
+    losses = [float(l.split("loss: ")[1]) for l in out0b.splitlines() if l.startswith("Train step ")]
+    assert all(v < 0.02 for v in losses), out0b
+    assert "done: local_steps=" in out0b and "done: local_steps=" in out1
+
+
+def test_more_ps_tasks_than_variables_global_step_and_exit():
+    """Round-1 advisor finding: with 5 ps tasks round-robin placement leaves ps 0 with `global_step` only (no variable,
+    no item); its counter is never incremented and it never saw `worker_done`. The counter of the first shard that
+    owns items is authoritative, every shard hears `worker_done`, and an item-less shard exits with the others."""
+    import torch  # noqa: F401
+    from dist_mnist_b200.models import mlp
+    from dist_mnist_b200.parallel.config import EngineConfig, OptimizerConfig
+    from dist_mnist_b200.session import InProcessCluster
+    from dist_mnist_b200.utils import data
+
+    ds = data.synthetic_mnist(512, seed=0)
+    spec = mlp.book_model(100)
+    cfg = EngineConfig(backend="cpu", nslots=4)
+    with InProcessCluster(spec, OptimizerConfig("adam", 1e-3), cfg, batch_size=32, num_ps=5) as cl:
+        w = cl.worker
+        assert cl.ps[0].shard.n_items == 0 and w.gs_owner != 0
+        for i in range(7):
+            out = w.step(ds.images[32 * i:32 * i + 32], ds.labels[32 * i:32 * i + 32])
+        w.wait_applied()
+        assert out.global_step == 7 and w.read_global_step() == 7
+        w.finish()
+        t0 = time.time()
+        while any(p.kernel_running() for p in cl.ps):
+            assert time.time() - t0 < 20, "a ps shard (the item-less one?) did not exit after every worker was done"
+            time.sleep(0.01)

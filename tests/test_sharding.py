@@ -60,3 +60,46 @@ def test_dw_tile_width_follows_the_compute_dtype():
     hid = lay.by_name["hid_w"]
     tiles = lay.shards[0].items[hid.item_base: hid.item_base + hid.n_items]
     assert [t.cols for t in tiles] == [32] * 24 + [16] and all(t.rows == 100 for t in tiles)
+
+
+def test_fused_tiling_covers_the_model_once_and_row_split_balances_the_big_variable():
+    spec = mlp.book_model(100)
+    for nps, strat in [(1, "round_robin"), (2, "round_robin"), (2, "row_split"), (3, "row_split"), (8, "row_split")]:
+        lay = sharding.build_layout(spec, nps, strat, dw_tile_n=32, engine="fused")
+        assert lay.engine == "fused" and len(lay.fused_slices) == 8
+        assert sum(s.kc_count for s in lay.fused_slices) == 25 and max(s.kc_count for s in lay.fused_slices) <= 4
+        # every element of every variable is owned by exactly one item of exactly one shard
+        total = 0
+        for sh in lay.shards:
+            seen = set()
+            for it in sh.items:
+                assert 0 <= it.flag < sh.n_flags
+                for r in range(it.rows):
+                    for c in range(0, it.cols, max(1, it.cols - 1)):   # corners of every row run
+                        key = it.offset + r * it.ld + c
+                        assert key not in seen
+                        seen.add(key)
+                total += it.rows * it.cols
+        assert total == spec.num_params
+        owners = {p.ps for p in lay.by_name["hid_w"].pieces}
+        if strat == "row_split":
+            assert owners == set(range(min(nps, 8)))
+            big = [b for _, b, _ in sharding.shard_bytes_summary(lay)]
+            assert max(big) < 0.75 * 318040 if nps >= 2 else True     # no shard holds (nearly) the whole model
+        else:
+            assert len(owners) == 1
+
+
+def test_engine_resolution_rules():
+    from dist_mnist_b200.parallel.config import EngineConfig
+    import pytest
+    cfg = EngineConfig(backend="cpu")
+    assert cfg.resolve_engine(mlp.book_model(100), 32) == "fused"
+    assert cfg.resolve_engine(mlp.book_model(100), 64) == "graph"       # batch > 32
+    assert cfg.resolve_engine(mlp.book_model(256), 32) == "graph"       # hidden > 128
+    assert cfg.resolve_engine(mlp.get_model("wide"), 32) == "graph"
+    assert EngineConfig(backend="cpu", dtype="bf16").resolve_engine(mlp.book_model(100), 32) == "graph"
+    with pytest.raises(ValueError):
+        EngineConfig(backend="cpu", engine="fused").resolve_engine(mlp.get_model("zhihu"), 32)
+    with pytest.raises(ValueError):
+        EngineConfig(backend="cpu", sharding="row_split").resolve_engine(mlp.get_model("zhihu"), 32)
