@@ -21,7 +21,7 @@ Numbers in the JSON line (all: max over ranks, throughput = workers x K / max el
              with `--strict_steps` (the next pull waits for the acknowledgement of the previous push).
   roofline : achieved fraction of the NVLink / HBM / tensor-core rooflines from MEASURED_PEAKS.json.
 
-Steps in flight: a worker keeps `--lanes` (default 8, the CLI's default too) steps in flight on its GPU — bounded-
+Steps in flight: a worker keeps `--lanes` (default 12, the CLI's default too) steps in flight on its GPU — bounded-
 staleness asynchronous SGD: every step still pulls, computes, pushes and is applied on the ps individually.
 """
 from __future__ import annotations
@@ -61,7 +61,7 @@ def parse_args(argv=None):
     p.add_argument("--sharding", choices=["round_robin", "byte_balanced", "row_split"], default="round_robin")
     p.add_argument("--engine", choices=["auto", "fused", "graph"], default="auto")
     p.add_argument("--nslots", type=int, default=0, help="mailbox slots per worker (0 = max(4 x lanes, 8))")
-    p.add_argument("--lanes", type=int, default=8,
+    p.add_argument("--lanes", type=int, default=12,
                    help="steps of one worker in flight on its GPU at once (async SGD; must be <= nslots)")
     p.add_argument("--strict_steps", action="store_true")
     p.add_argument("--graph_steps", type=int, default=0,
@@ -224,6 +224,10 @@ def main(argv=None) -> int:
                 rdv_any.wait_count(f"bench/{ph}/quiet", n_workers, poll_s=0.0002)
         for ps in ps_list:
             ps.stop()
+            if os.environ.get("DM_PS_STATS") == "1":   # serve-kernel counters of the region that just ended (stderr)
+                st = ps.serve_stats(reset=True)
+                if st:
+                    print(f"[ps_stats] sync {ph} rank={rank} shard={ps.task_index} {json.dumps(st)}", file=sys.stderr, flush=True)
         barrier()
         torch.cuda.synchronize()
         if restart:
@@ -242,27 +246,37 @@ def main(argv=None) -> int:
         xrow, yrow = dev_x.shape[1] * dev_x.element_size(), dev_y.shape[1] * 4
     cursor = [0]
 
-    def resident_steps(n):
-        worker.run_resident(n, dev_x.data_ptr(), dev_y.data_ptr(), xrow, yrow, n_rows, cursor[0])
+    def resident_steps(n, wait_applied=False, timed=False):
+        worker.run_resident(n, dev_x.data_ptr(), dev_y.data_ptr(), xrow, yrow, n_rows, cursor[0], wait_applied=wait_applied,
+                            **({"timed": True} if timed else {}))
         cursor[0] += n
 
     def device_timed(n):
         """n steps, CUDA-event timed on the compute stream incl. the ps acknowledgement of the last push (ms)."""
+        if engine == "fused":
+            # one launch; its tail waits for the acknowledgement of the last push; the two CUDA events are recorded by
+            # the native executor on the launching stream immediately before / after the launch
+            t_host = time.perf_counter()
+            resident_steps(n, wait_applied=True, timed=True)
+            enq_ms = (time.perf_counter() - t_host) * 1e3
+            return worker.last_elapsed_ms(), enq_ms
         timer = StreamTimer(worker.compute_stream, local_rank)
         timer.start()
         worker.fork_lanes()   # graph engine: no lane starts a timed step before the start event
         t_host = time.perf_counter()
-        resident_steps(n)
+        fused = engine == "fused"
+        resident_steps(n, wait_applied=fused)   # fused engine: the launch ends with the acknowledgement wait itself
         enq_ms = (time.perf_counter() - t_host) * 1e3
-        worker.enqueue_wait_ack()
+        if not fused:
+            worker.enqueue_wait_ack()
         timer.stop()
         return timer.elapsed_ms(), enq_ms
 
     def host_fed(n):
         """n steps through Worker.run_steps (gather + H2D + kernels + result read-back), wall clock (s)."""
         t0 = time.perf_counter()
-        outs = worker.run_steps(n, loaders["l"])   # returns when every result has been read back
-        worker.wait_applied()                       # ... and every push of the region is applied on the ps
+        # returns when every result has been read back and every push of the region is applied on the ps
+        outs = worker.run_steps(n, loaders["l"], wait_applied=True)
         dt = time.perf_counter() - t0
         assert len(outs) == n, (len(outs), n)
         return dt
@@ -287,7 +301,7 @@ def main(argv=None) -> int:
     if worker is not None:
         launches_before = worker.kernel_launches()
         elapsed_ms, host_enqueue_ms = device_timed(K)
-        launches = worker.kernel_launches() - launches_before + 1   # + the acknowledgement-wait kernel
+        launches = worker.kernel_launches() - launches_before + (0 if engine == "fused" else 1)   # (+ wait_ack kernel)
     full_sync()
     if os.environ.get("DM_FUSED_DEBUG_TS") == "1" and worker is not None and getattr(worker, "_fx_dbg", None) is not None:
         from bench_tools.fused_phases import print_stamps   # in-kernel phase stamps of the timed launch (stderr)
@@ -339,10 +353,6 @@ def main(argv=None) -> int:
     final_step = worker.read_global_step() if (worker is not None and worker.is_chief) else 0
     full_sync(restart=False)   # serve kernels stay down from here on: torch/NCCL ops below are safe
     clocks = sampler.stop() if sampler is not None else None
-    for ps in ps_list:   # DM_PS_STATS=1: serve-kernel statistics of this rank's shard (diagnostics, stderr)
-        st = ps.serve_stats()
-        if st:
-            print(f"[ps_stats] rank={rank} shard={ps.task_index} {json.dumps(st)}", file=sys.stderr, flush=True)
 
     # ---------------- reduce over ranks ----------------
     kps = worker.kernels_per_step if worker is not None else 0

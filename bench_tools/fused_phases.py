@@ -31,6 +31,12 @@ def print_stamps(buf, tag):
               + (f", next step starts {nxt} cyc after this one" if nxt is not None else ""))
 
 
+    g = [int(buf[60]), int(buf[61]), int(buf[63])]
+    if g[0] and g[1]:
+        print(f"  globaltimer: kernel entry -> first step claimed {(g[1] - g[0]) / 1e3:.2f} us"
+              + (f"; entry -> last cluster re-armed / acks in {(g[2] - g[0]) / 1e3:.2f} us" if g[2] > g[0] else ""))
+
+
 def main():
     os.environ["DM_FUSED_DEBUG_TS"] = "1"
     ds = data.synthetic_mnist(8192, seed=0)

@@ -145,6 +145,8 @@ class FusedParams(C.Structure):
         ("ps_global_step", C.c_void_p),
         ("results", C.c_void_p),
         ("debug_ts", C.c_void_p),
+        ("exit_counter", C.c_void_p),
+        ("clear_stop", C.c_uint32), ("wait_acks", C.c_uint32),
     ]
 
 
@@ -274,8 +276,9 @@ def _declare(l: C.CDLL) -> None:
         "dm_fexec_drain": (i, [vp]),
         "dm_fexec_debug": (i, [vp, vp]),
         "dm_fexec_steps_host": (i, [vp, vp, vp, u32, vp, C.POINTER(u32)]),
-        "dm_fexec_run": (i, [vp, vp, u64, vp, u32, C.POINTER(u64)]),
-        "dm_fexec_run_resident": (i, [vp, vp, vp, u64, u64, u64, u64]),
+        "dm_fexec_run": (i, [vp, vp, u64, vp, u32, C.POINTER(u64), i]),
+        "dm_fexec_run_resident": (i, [vp, vp, vp, u64, u64, u64, u64, i, i]),
+        "dm_fexec_last_elapsed_ms": (i, [vp, C.POINTER(C.c_float)]),
         "dm_fexec_resident_results": (i, [vp, vp, u64, C.POINTER(u64)]),
         "dm_fexec_destroy": (i, [vp]),
     }

@@ -35,7 +35,7 @@ from .utils import data as data_utils
 from .utils.metrics import TrainMetricsWriter
 
 
-DEFAULT_LANES = 8    # the engine's default (bench.py uses the same); --lanes 1 reproduces the reference's sequential loop
+DEFAULT_LANES = 12   # the engine's default (bench.py uses the same); --lanes 1 reproduces the reference's sequential loop
 
 
 def engine_config_from_args(args, backend: str) -> EngineConfig:

@@ -20,12 +20,15 @@
 // and sanitizers that serialise kernels.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -59,10 +62,13 @@ inline void cpu_relax() {
 // ---------------------------------------------------------------------------------------------
 struct GatherTask {
   const dm::BatchLoader* loader;
-  std::vector<uint32_t> idx;   // batch row indices (planned by the submitting thread: the loader stays sequential)
+  std::shared_ptr<std::vector<uint32_t>> idx;   // batch row indices (planned by the submitting thread: the loader
+                                                // stays sequential); shared by the sub-tasks of one batch
+  int r0, r1;                   // rows of the batch this task copies (a batch is split over several threads: the
+                                // gather is DRAM-latency bound, ~2 us per 3 KB row)
   uint8_t* x_dst;
   uint8_t* y_dst;
-  std::atomic<uint32_t>* done;  // incremented when the batch is in place
+  std::atomic<uint32_t>* done;  // += rows copied
 };
 
 struct GatherPool {
@@ -73,6 +79,7 @@ struct GatherPool {
   std::atomic<int> active{0};     // > 0 while some run is in progress: workers spin instead of sleeping
   std::atomic<uint64_t> posted{0}, taken{0};
   bool quit = false;
+  int spin_grace_ms = 20;
 
   void start(int n) {
     for (int t = 0; t < n; ++t) threads.emplace_back([this] { loop(); });
@@ -104,19 +111,26 @@ struct GatherPool {
     cv.notify_one();
   }
   static void run_task(GatherTask* t) {
-    t->loader->copy(t->idx.data(), t->x_dst, t->y_dst);
+    t->loader->copy_rows(t->idx->data(), t->r0, t->r1, t->x_dst, t->y_dst);
     std::atomic<uint32_t>* d = t->done;
+    const uint32_t rows = static_cast<uint32_t>(t->r1 - t->r0);
     delete t;
-    d->fetch_add(1, std::memory_order_release);
+    d->fetch_add(rows, std::memory_order_release);
   }
   void loop() {
+    // Spin while a run is active and for a grace period after the last one (a training loop calls run() back to back:
+    // waking a parked thread costs tens of microseconds — more than gathering a whole batch); park on the condition
+    // variable only when the executor has really gone idle.
+    auto last_active = std::chrono::steady_clock::now();
     for (;;) {
       GatherTask* t = try_pop();
-      if (t != nullptr) { run_task(t); continue; }
-      if (active.load(std::memory_order_acquire) > 0) { cpu_relax(); continue; }
+      if (t != nullptr) { run_task(t); last_active = std::chrono::steady_clock::now(); continue; }
+      if (active.load(std::memory_order_acquire) > 0) { cpu_relax(); last_active = std::chrono::steady_clock::now(); continue; }
+      if (std::chrono::steady_clock::now() - last_active < std::chrono::milliseconds(spin_grace_ms)) { cpu_relax(); continue; }
       std::unique_lock<std::mutex> lk(mu);
       cv.wait(lk, [this] { return quit || !queue.empty() || active.load(std::memory_order_acquire) > 0; });
       if (quit && queue.empty()) return;
+      last_active = std::chrono::steady_clock::now();
     }
   }
 };
@@ -124,6 +138,7 @@ struct GatherPool {
 constexpr int kChunkMax = 16;   // steps per chunk buffer
 constexpr int kBuffers = 4;     // chunk buffers in rotation
 constexpr int kRowsPerSlot = 32;
+constexpr int kRowsPerTask = 8;   // rows of a batch gathered by one pool task
 
 struct ChunkBuf {
   cudaEvent_t copied = nullptr, done = nullptr;
@@ -154,20 +169,26 @@ struct FusedExec {
   uint64_t launches = 0;
   ChunkBuf bufs[kBuffers];
   GatherPool pool;
+  cudaEvent_t t_start = nullptr, t_stop = nullptr;   // timing events of a timed resident launch
   cudaEvent_t last_done = nullptr;  // completion of the most recent launch
   uint64_t last_n = 0;              // steps requested by the most recent resident launch
   dm::StepResult* last_results = nullptr;
 
+  // The kernel re-arms its own launch state (step counter, exit counter, optionally the stop word) when its last cluster
+  // exits, so a launch is exactly one stream operation. `clear_stop`: last launch of a run; `wait_acks`: the launch
+  // returns only after the ps has applied every push made so far.
   int launch(const dm::FusedMaps& m, dm::FusedParams p, uint32_t n_steps, dm::StepResult* results, uint32_t stop_at,
-             bool reset_stop) {
+             bool clear_stop, bool wait_acks = false) {
     p.n_steps = n_steps;
     p.seq_base = static_cast<uint32_t>(steps_done);
     p.stop_at = stop_at;
     p.step_counter = ctl_dev;
     p.stop_word = ctl_dev + 1;
     p.seq_word = ctl_dev + 2;
+    p.exit_counter = ctl_dev + 3;
+    p.clear_stop = clear_stop ? 1u : 0u;
+    p.wait_acks = wait_acks ? 1u : 0u;
     p.results = results;
-    FX_CUDA(cudaMemcpyAsync(ctl_dev, zeros_pin, reset_stop ? 8 : 4, cudaMemcpyHostToDevice, compute));
     FX_CUDA(dm::launch_fused_step(m, p, lanes, compute));
     ++launches;
     return 0;
@@ -229,9 +250,12 @@ int dm_fexec_create(int device, int lanes, int I, int C, int batch, void** out) 
     FX_CUDA(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
   }
   FX_CUDA(cudaEventCreateWithFlags(&ex->last_done, cudaEventDisableTiming));
+  FX_CUDA(cudaEventCreate(&ex->t_start));
+  FX_CUDA(cudaEventCreate(&ex->t_stop));
   if (ex->ensure_big(1u << 16) != 0) return -1;   // up front: no pinned allocation while a persistent ps kernel is resident
   if (const char* e = getenv("DM_GATHER_THREADS")) ex->n_threads = std::max(1, atoi(e));
-  else ex->n_threads = static_cast<int>(std::min<unsigned>(8u, std::max(2u, std::thread::hardware_concurrency() / 2)));
+  else ex->n_threads = static_cast<int>(std::min<unsigned>(12u, std::max(2u, std::thread::hardware_concurrency() / 2)));
+  if (const char* e = getenv("DM_GATHER_SPIN_MS")) ex->pool.spin_grace_ms = std::max(0, atoi(e));
   ex->pool.start(ex->n_threads);
   *out = ex;
   return 0;
@@ -335,8 +359,9 @@ int dm_fexec_steps_host(void* h, const void* x_host, const void* y_host, uint32_
 // The native train loop: n_steps x { next_batch -> pinned staging -> H2D -> fused step -> result }, chunked and
 // pipelined as described in the file header. stop_at_global_step > 0: StopAtStepHook semantics (reference DS:101) —
 // no step is started once a finished step has reported global_step >= that value; *n_done = steps actually run.
+// wait_acks != 0 (and no stop condition): the last chunk's launch returns only after the ps has acknowledged every push.
 int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uint32_t stop_at_global_step,
-                 uint64_t* n_done) {
+                 uint64_t* n_done, int wait_acks) {
   FusedExec* ex = static_cast<FusedExec*>(h);
   dm::BatchLoader* ld = static_cast<dm::BatchLoader*>(loader);
   dm::StepResult* out = static_cast<dm::StepResult*>(out_results);
@@ -360,6 +385,9 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
   const size_t nchunks = sizes.size();
   std::vector<uint64_t> first(nchunks + 1, 0);
   for (size_t c = 0; c < nchunks; ++c) first[c + 1] = first[c] + sizes[c];
+  const bool trace = getenv("DM_FEXEC_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto us_since = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(); };
   ex->pool.active.fetch_add(1, std::memory_order_release);
   ex->pool.cv.notify_all();
   uint64_t total_done = 0;
@@ -406,14 +434,19 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
       const size_t slot0 = (c % kBuffers) * kChunkMax;
       memset(ex->res_chunks + slot0, 0, sizes[c] * sizeof(dm::StepResult));
       for (uint32_t i = 0; i < sizes[c]; ++i) {
-        GatherTask* t = new GatherTask();
-        t->loader = ld;
-        t->idx.resize(ld->batch);
-        ld->plan(t->idx.data());
-        t->x_dst = ex->x_stage + (slot0 + i) * ex->x_slot_bytes;
-        t->y_dst = ex->y_stage + (slot0 + i) * ex->y_slot_bytes;
-        t->done = &b.gathered;
-        ex->pool.post(t);
+        auto idx = std::make_shared<std::vector<uint32_t>>(ld->batch);
+        ld->plan(idx->data());
+        for (int r0 = 0; r0 < ld->batch; r0 += kRowsPerTask) {
+          GatherTask* t = new GatherTask();
+          t->loader = ld;
+          t->idx = idx;
+          t->r0 = r0;
+          t->r1 = std::min(ld->batch, r0 + kRowsPerTask);
+          t->x_dst = ex->x_stage + (slot0 + i) * ex->x_slot_bytes;
+          t->y_dst = ex->y_stage + (slot0 + i) * ex->y_slot_bytes;
+          t->done = &b.gathered;
+          ex->pool.post(t);
+        }
       }
       ++next_gather;
     }
@@ -422,7 +455,7 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
     {
       const size_t c = next_launch;
       ChunkBuf& b = ex->bufs[c % kBuffers];
-      while (b.gathered.load(std::memory_order_acquire) < b.n) {
+      while (b.gathered.load(std::memory_order_acquire) < b.n * static_cast<uint32_t>(ld->batch)) {
         GatherTask* t = ex->pool.try_pop();
         if (t != nullptr) GatherPool::run_task(t);
         else cpu_relax();
@@ -443,9 +476,12 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
       // by the stop condition the (persistent) stop word keeps every later chunk from claiming anything
       const uint64_t saved = ex->steps_done;
       ex->steps_done = saved + first[c];
-      const int lrc = ex->launch(ex->maps, p, b.n, ex->res_chunks + slot0, stop_at_global_step, first_launch);
+      const int lrc = ex->launch(ex->maps, p, b.n, ex->res_chunks + slot0, stop_at_global_step,
+                                 /*clear_stop=*/stop_at_global_step == 0,
+                                 /*wait_acks=*/wait_acks != 0 && stop_at_global_step == 0 && c + 1 == nchunks);
       ex->steps_done = saved;
       if (lrc != 0) { rc = -1; break; }
+      if (trace) fprintf(stderr, "[fexec] chunk %zu (%u steps) launched at +%.1f us\n", c, b.n, us_since());
       first_launch = false;
       e = cudaEventRecord(b.done, ex->compute);
       if (e != cudaSuccess) { rc = fxfail("cudaEventRecord", e); break; }
@@ -467,7 +503,7 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
   }
   for (size_t c = next_launch; c < next_gather; ++c) {   // wait for outstanding gather tasks of unlaunched chunks
     ChunkBuf& b = ex->bufs[c % kBuffers];
-    while (b.gathered.load(std::memory_order_acquire) < b.n) {
+    while (b.gathered.load(std::memory_order_acquire) < b.n * static_cast<uint32_t>(ld->batch)) {
       GatherTask* t = ex->pool.try_pop();
       if (t != nullptr) GatherPool::run_task(t);
       else cpu_relax();
@@ -477,6 +513,10 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
   ex->pool.active.fetch_sub(1, std::memory_order_release);
   if (rc != 0) return rc;
   FX_CUDA(cudaStreamSynchronize(ex->compute));
+  if (trace) fprintf(stderr, "[fexec] run of %llu steps drained at +%.1f us (%d gather threads)\n",
+                     static_cast<unsigned long long>(n_steps), us_since(), ex->n_threads);
+  if (stop_at_global_step != 0)   // the stop word had to survive across the chunks of this run: clear it now
+    FX_CUDA(cudaMemcpyAsync(ex->ctl_dev + 1, ex->zeros_pin, 4, cudaMemcpyHostToDevice, ex->compute));
   ex->steps_done += total_done;
   if (n_done) *n_done = total_done;
   return 0;
@@ -485,8 +525,10 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
 // One launch for n_steps over a device-resident dataset: `maps` are tensor maps over the dataset, the batch of step s
 // is rows [(row_start + s * row_stride) % row_wrap, +32). Asynchronous: returns after enqueueing (dm_fexec_drain /
 // dm_fexec_resident_results complete it).
+// `timed` != 0: the launch is bracketed by two CUDA events recorded on the compute stream immediately before and after
+// it (no interpreter time in between); dm_fexec_last_elapsed_ms returns their distance.
 int dm_fexec_run_resident(void* h, const void* maps, const void* y_base, uint64_t row_start, uint64_t row_stride,
-                          uint64_t row_wrap, uint64_t n_steps) {
+                          uint64_t row_wrap, uint64_t n_steps, int wait_acks, int timed) {
   FusedExec* ex = static_cast<FusedExec*>(h);
   if (!ex->have_params || n_steps == 0 || n_steps > 0xFFFFFFF0ull) { g_fx_err = "run_resident: bad arguments"; return -1; }
   if (ex->last_results == ex->res_big && ex->last_n != 0) FX_CUDA(cudaEventSynchronize(ex->last_done));
@@ -499,11 +541,21 @@ int dm_fexec_run_resident(void* h, const void* maps, const void* y_base, uint64_
   p.row_start = row_start;
   p.row_stride = row_stride;
   p.row_wrap = row_wrap;
-  if (ex->launch(m, p, static_cast<uint32_t>(n_steps), ex->res_big, 0, true) != 0) return -1;
+  if (timed) FX_CUDA(cudaEventRecord(ex->t_start, ex->compute));
+  if (ex->launch(m, p, static_cast<uint32_t>(n_steps), ex->res_big, 0, true, wait_acks != 0) != 0) return -1;
+  if (timed) FX_CUDA(cudaEventRecord(ex->t_stop, ex->compute));
   FX_CUDA(cudaEventRecord(ex->last_done, ex->compute));
   ex->steps_done += n_steps;   // no stop condition on this path: every step runs
   ex->last_n = n_steps;
   ex->last_results = ex->res_big;
+  return 0;
+}
+
+// Device time of the most recent timed resident launch (waits for it).
+int dm_fexec_last_elapsed_ms(void* h, float* ms) {
+  FusedExec* ex = static_cast<FusedExec*>(h);
+  FX_CUDA(cudaEventSynchronize(ex->t_stop));
+  FX_CUDA(cudaEventElapsedTime(ms, ex->t_start, ex->t_stop));
   return 0;
 }
 
@@ -529,6 +581,8 @@ int dm_fexec_destroy(void* h) {
     cudaEventDestroy(b.done);
   }
   cudaEventDestroy(ex->last_done);
+  cudaEventDestroy(ex->t_start);
+  cudaEventDestroy(ex->t_stop);
   cudaFree(ex->x_dev);
   cudaFree(ex->y_dev);
   cudaFree(ex->ctl_dev);

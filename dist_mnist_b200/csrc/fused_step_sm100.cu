@@ -137,6 +137,8 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 4);
   volatile uint32_t* ctl_next = reinterpret_cast<volatile uint32_t*>(smem + kOffCtl);
 
+  if (p.debug_ts != nullptr && blockIdx.y == 0 && rank == 0 && threadIdx.x == 0)
+    p.debug_ts[60] = static_cast<long long>(globaltimer_ns());                                 // kernel entry
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&maps.w[rank]);
     prefetch_tensormap(&maps.xk);
@@ -177,6 +179,7 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
   uint32_t cur = ctl_next[0];
 
   const bool dbg = p.debug_ts != nullptr && blockIdx.y == 0 && rank == 0;
+  if (dbg && threadIdx.x == 0) p.debug_ts[61] = static_cast<long long>(globaltimer_ns());   // first step claimed
   const bool mailbox = p.shard[0].push.mode == PUSH_MAILBOX;
   const int H = p.H, C = p.C, B = p.B;
   const uint32_t wl_bytes = (static_cast<uint32_t>(C * H) * 4u + 15u) & ~15u;   // bulk copies move 16-byte multiples
@@ -636,6 +639,21 @@ fused_step_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant_
   tcgen05_fence_after();
   if (warp == 1) tmem_dealloc(tmem_base, kFsTmemCols);
   cluster_sync_all();   // nobody leaves while a peer might still address its shared memory
+  if (rank == 0 && threadIdx.x == 0) {
+    // The last cluster to finish re-arms the launch state (no host-side memset / copy between launches) and, when asked
+    // to, waits for the ps acknowledgement of every push made so far — every other cluster has published its steps
+    // before it got here, so *seq_word is final.
+    __threadfence();
+    if (atomicAdd(p.exit_counter, 1u) + 1u == gridDim.y) {
+      __threadfence();
+      if (p.wait_acks && p.shard[0].push.mode == PUSH_MAILBOX)
+        fs_wait_acks(p, *reinterpret_cast<volatile uint32_t*>(p.seq_word), "end of launch");
+      *p.step_counter = 0u;
+      *p.exit_counter = 0u;
+      if (p.clear_stop) *p.stop_word = 0u;
+      if (dbg) p.debug_ts[63] = static_cast<long long>(globaltimer_ns());
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -48,6 +48,13 @@ struct BatchLoader {
       memcpy(y_dst + r * y_dst_stride, labels + static_cast<size_t>(idx[r]) * y_row_bytes, y_row_bytes);
     }
   }
+  // rows [r0, r1) of a planned batch (a batch can be gathered by several threads)
+  void copy_rows(const uint32_t* idx, int r0, int r1, uint8_t* x_dst, uint8_t* y_dst) const {
+    for (int r = r0; r < r1; ++r) {
+      memcpy(x_dst + r * x_dst_stride, images + static_cast<size_t>(idx[r]) * x_row_bytes, x_row_bytes);
+      memcpy(y_dst + r * y_dst_stride, labels + static_cast<size_t>(idx[r]) * y_row_bytes, y_row_bytes);
+    }
+  }
   void next(uint8_t* x_dst, uint8_t* y_dst) {
     std::vector<uint32_t> idx(batch);
     plan(idx.data());

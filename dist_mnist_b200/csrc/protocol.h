@@ -236,12 +236,16 @@ struct FusedParams {
   uint32_t seq_base;       // push sequence number of step s is seq_base + s + 1
   uint32_t nslots;
   uint32_t stop_at;        // > 0: no further steps are claimed once a step reports global_step >= stop_at
-  uint32_t* step_counter;  // device word, zeroed before the launch
-  uint32_t* stop_word;     // device word, zeroed before the launch
+  uint32_t* step_counter;  // device word: next unclaimed step of the launch; the last cluster to exit zeroes it again
+  uint32_t* stop_word;     // device word, zeroed by the last cluster to exit when `clear_stop` is set
   uint32_t* seq_word;      // device word: total pushes made by this worker (advanced at the end of every step)
   uint32_t* ps_global_step;  // atomic mode: peer pointer to the shared step counter
   StepResult* results;     // [n_steps] pinned host memory, written by the kernel
   long long* debug_ts;     // optional phase stamps of cluster 0 / CTA 0
+  uint32_t* exit_counter;  // device word: clusters that have finished (self-resetting)
+  uint32_t clear_stop;     // 1: the last cluster to exit zeroes *stop_word (last launch of a run)
+  uint32_t wait_acks;      // 1: the last cluster to exit returns only after every shard has acknowledged every push made
+                           //    so far (the launch then covers the ps-side apply of its last step: timed regions)
 };
 
 }  // namespace dm

@@ -328,14 +328,19 @@ class ParameterServer:
                 self._cpu_handle = None
         self._serving = False
 
-    def serve_stats(self) -> Optional[dict]:
-        """Aggregated serve-kernel statistics (DM_PS_STATS=1; valid after stop()): per-pass averages over CTAs."""
+    def serve_stats(self, reset: bool = False) -> Optional[dict]:
+        """Aggregated serve-kernel statistics (DM_PS_STATS=1; valid after stop()): per-pass averages over CTAs.
+        `reset`: zero the counters afterwards (per-region statistics)."""
         if self.cfg.backend != "cuda" or os.environ.get("DM_PS_STATS") != "1":
             return None
         n = 160 * 8
         host = (C.c_uint64 * n)()
         N.check(self.lib.dm_memcpy_async(C.addressof(host), self.seg.addr("stats"), 8 * n, None))
         N.check(self.lib.dm_stream_sync(None))
+        if reset:
+            zeros = (C.c_uint64 * n)()
+            N.check(self.lib.dm_memcpy_async(self.seg.addr("stats"), C.addressof(zeros), 8 * n, None))
+            N.check(self.lib.dm_stream_sync(None))
         rows = [list(host[i * 8:(i + 1) * 8]) for i in range(160) if host[i * 8] or host[i * 8 + 4]]
         if not rows:
             return None

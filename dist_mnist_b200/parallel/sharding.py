@@ -235,6 +235,12 @@ def build_layout(spec: MLPSpec, num_ps: int, strategy: str = "round_robin", dw_t
             role = "last_w" if last else "hidden_w"
             rows, cols = v.shape
             ld = cols if last else padded_ld(cols)
+            if engine == "fused" and not last:
+                # Fused tiling: rows are padded to whole 128-byte lines (32 floats). Every 128-byte row segment of a
+                # pulled W tile / pushed dW tile is then ONE aligned line on the ps shard instead of two half lines:
+                # half the NVLink packets and no partial-line writes into the mailbox (with ld = 784 the ps ingress
+                # took 10-25 us to acknowledge a tile once three workers pushed concurrently).
+                ld = _round_up(cols, 32)
             span = rows * ld
         else:
             role = "last_b" if last else "hidden_b"

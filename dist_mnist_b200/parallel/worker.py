@@ -734,7 +734,7 @@ class Worker:
         return t.value
 
     def run_resident(self, n_steps: int, x_base_ptr: int, y_base_ptr: int, x_row_bytes: int, y_row_bytes: int,
-                     n_rows: int, start: int = 0) -> None:
+                     n_rows: int, start: int = 0, wait_applied: bool = False, timed: bool = False) -> None:
         """Native loop over a device-resident dataset: step i trains on rows ((start + i) * batch) % n_rows ..
         (contiguous). Graph engine: copied device-to-device into the slot buffers; fused engine: one launch whose
         TMA loads read the rows straight out of the dataset. Results stay in the executor."""
@@ -744,12 +744,23 @@ class Worker:
             key = (x_base_ptr, n_rows)
             if key not in self._fx_ds_maps:
                 self._fx_ds_maps[key] = self._fused_maps(x_base_ptr, n_rows + N.FUSED_ROWS_PER_SLOT)
+            # wait_applied: the launch itself ends with the wait for the ps acknowledgement of its last push (no extra
+            # kernel); only meaningful when a persistent ps kernel is serving
+            wa = int(wait_applied and not self._ps_local)
             N.check(self.lib.dm_fexec_run_resident(self._fexec, C.addressof(self._fx_ds_maps[key]), y_base_ptr,
-                                                   start * self.batch, self.batch, n_rows, n_steps), "run resident")
+                                                   start * self.batch, self.batch, n_rows, n_steps, wa, int(timed)),
+                    "run resident")
             self._serve_local()
             return
         N.check(self.lib.dm_exec_run_resident(self._exec, n_steps, x_base_ptr, y_base_ptr, x_row_bytes, y_row_bytes,
                                               n_rows, self.batch, start), "run resident")
+
+    def last_elapsed_ms(self) -> float:
+        """Fused engine: device time (CUDA events recorded natively right around the launch) of the most recent
+        `run_resident(..., timed=True)`."""
+        ms = C.c_float(0.0)
+        N.check(self.lib.dm_fexec_last_elapsed_ms(self._fexec, C.byref(ms)), "elapsed")
+        return float(ms.value)
 
     def result(self, ticket: int, wait: bool = True) -> Optional[StepOutput]:
         if self.engine == "fused" and self.cfg.backend == "cuda":
@@ -776,8 +787,11 @@ class Worker:
         """Native `next_batch` loader over a host dataset (kept alive by the returned object)."""
         return NativeLoader(self, images, labels, seed, shuffle)
 
-    def run_steps(self, n_steps: int, loader: "NativeLoader", stop_at_global_step: int = 0) -> Sequence[StepOutput]:
-        """Native train loop: n_steps x (next_batch -> H2D -> step graph -> result D2H)."""
+    def run_steps(self, n_steps: int, loader: "NativeLoader", stop_at_global_step: int = 0,
+                  wait_applied: bool = False) -> Sequence[StepOutput]:
+        """Native train loop: n_steps x (next_batch -> H2D -> step kernels -> result D2H). `wait_applied`: return only
+        once every push of the run has been applied by the ps tasks (fused engine: the tail of the last launch waits
+        for the acknowledgements; otherwise `wait_applied()` is called)."""
         if self.cfg.backend != "cuda":
             out = []
             for _ in range(n_steps):
@@ -786,16 +800,23 @@ class Worker:
                 out.append(r)
                 if stop_at_global_step and r.global_step >= stop_at_global_step:
                     break
+            if wait_applied:
+                self.wait_applied()
             return out
         res = (N.StepResult * n_steps)()
         done = C.c_uint64()
         if self.engine == "fused":
+            in_kernel = wait_applied and not stop_at_global_step and not self._ps_local
             N.check(self.lib.dm_fexec_run(self._fexec, loader.handle, n_steps, C.addressof(res), stop_at_global_step,
-                                          C.byref(done)), "fused exec run")
+                                          C.byref(done), int(in_kernel)), "fused exec run")
+            if in_kernel:
+                wait_applied = False
         else:
             N.check(self.lib.dm_exec_run(self._exec, loader.handle, n_steps, C.addressof(res), stop_at_global_step,
                                          C.byref(done)), "exec run")
         self._serve_local()
+        if wait_applied:
+            self.wait_applied()
         raw = np.frombuffer(res, dtype=_STEP_DTYPE, count=n_steps)[: done.value]   # keeps `res` alive
         return StepOutputs(raw)
 

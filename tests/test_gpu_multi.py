@@ -61,7 +61,7 @@ def test_bench_two_gpus_contract():
     line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     d = json.loads(line)
     assert d["n_gpus"] == 2 and d["value"] > 0 and d["e2e"]["value"] > 0
-    # fused engine: one persistent kernel launch runs all 300 steps (+ the acknowledgement-wait kernel)
-    assert d["gpu_launches"] >= 2 and d["gpu_launches"] * d["steps_per_launch"] >= 300
+    # fused engine: one persistent kernel launch runs all 300 steps (the acknowledgement wait is its tail)
+    assert d["gpu_launches"] >= 1 and d["gpu_launches"] * d["steps_per_launch"] >= 300
     assert d["config"]["global_step_after_run"] >= 300 and d["config"]["engine"] == "fused"
     assert d["parity"]["value_device_timed"] > 0
