@@ -83,6 +83,14 @@ def engine_config(args, backend: str = "cuda"):
                         engine=args.engine, strict_steps=args.strict_steps, ps_row_blocks=args.ps_row_blocks)
 
 
+def _usable_cores():
+    try:
+        from dist_mnist_b200.parallel.worker import usable_cores
+        return usable_cores()
+    except Exception:
+        return None
+
+
 def load_peaks() -> dict:
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")
     try:
@@ -418,6 +426,9 @@ def main(argv=None) -> int:
                              "parameters (0.3 MB) stay L2-resident as in real training",
                 "global_step_after_run": int(mx[5]),
                 "barrier_sync_ms": [round(v, 2) for v in sync_ms[:3]],
+                "host_cores": os.cpu_count(),
+                "usable_cores": _usable_cores(),
+                "gather_threads_per_worker": os.environ.get("DM_GATHER_THREADS"),
             },
             "clocks": clocks,
             "gpu_launches": int(sm[2]),

@@ -79,7 +79,7 @@ struct GatherPool {
   std::atomic<int> active{0};     // > 0 while some run is in progress: workers spin instead of sleeping
   std::atomic<uint64_t> posted{0}, taken{0};
   bool quit = false;
-  int spin_grace_ms = 20;
+  int spin_grace_ms = 1;
 
   void start(int n) {
     for (int t = 0; t < n; ++t) threads.emplace_back([this] { loop(); });
@@ -254,7 +254,7 @@ int dm_fexec_create(int device, int lanes, int I, int C, int batch, void** out) 
   FX_CUDA(cudaEventCreate(&ex->t_stop));
   if (ex->ensure_big(1u << 16) != 0) return -1;   // up front: no pinned allocation while a persistent ps kernel is resident
   if (const char* e = getenv("DM_GATHER_THREADS")) ex->n_threads = std::max(1, atoi(e));
-  else ex->n_threads = static_cast<int>(std::min<unsigned>(12u, std::max(2u, std::thread::hardware_concurrency() / 2)));
+  else ex->n_threads = static_cast<int>(std::min<unsigned>(8u, std::max(2u, std::thread::hardware_concurrency() / 2)));
   if (const char* e = getenv("DM_GATHER_SPIN_MS")) ex->pool.spin_grace_ms = std::max(0, atoi(e));
   ex->pool.start(ex->n_threads);
   *out = ex;

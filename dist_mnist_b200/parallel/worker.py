@@ -80,6 +80,31 @@ def _round_up(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
 
+def usable_cores() -> int:
+    """CPU cores this process may really use: the affinity mask, further limited by a cgroup CPU quota (a container
+    can see 128 cores and be throttled to a fraction of them — spinning helper threads beyond the quota stall the
+    whole process for the rest of every scheduler period)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 8
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // period))
+            break
+        except Exception:
+            continue
+    return n
+
+
 class Worker:
     def __init__(self, cluster: ClusterSpec, task_index: int, spec: MLPSpec, opt: OptimizerConfig,
                  cfg: EngineConfig, batch_size: int = 32, device: int = 0, rdv: Optional[Rendezvous] = None,
@@ -602,6 +627,11 @@ class Worker:
         N.check(self.lib.dm_fused_max_lanes(self.device, C.byref(max_lanes)), "fused occupancy")
         lanes = max(1, min(cfg.lanes, max_lanes.value if max_lanes.value > 0 else cfg.lanes))
         self.fused_lanes = lanes
+        if "DM_GATHER_THREADS" not in os.environ:
+            # the gather pool spins while a run is active: share the host's cores between the worker processes of
+            # this node (torchrun exports LOCAL_WORLD_SIZE; a stand-alone task assumes it has the node to itself)
+            local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+            os.environ["DM_GATHER_THREADS"] = str(max(2, min(8, usable_cores() // (2 * local_world) - 1)))
         out = C.c_void_p()
         N.check(self.lib.dm_fexec_create(self.device, lanes, I, Cn, self.batch, C.byref(out)), "fused exec create")
         self._fexec = out.value
