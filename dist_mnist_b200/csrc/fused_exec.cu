@@ -254,7 +254,7 @@ int dm_fexec_create(int device, int lanes, int I, int C, int batch, void** out) 
   FX_CUDA(cudaEventCreate(&ex->t_stop));
   if (ex->ensure_big(1u << 16) != 0) return -1;   // up front: no pinned allocation while a persistent ps kernel is resident
   if (const char* e = getenv("DM_GATHER_THREADS")) ex->n_threads = std::max(1, atoi(e));
-  else ex->n_threads = static_cast<int>(std::min<unsigned>(8u, std::max(2u, std::thread::hardware_concurrency() / 2)));
+  else ex->n_threads = static_cast<int>(std::min<unsigned>(8u, std::max(2u, std::thread::hardware_concurrency() / 4)));
   if (const char* e = getenv("DM_GATHER_SPIN_MS")) ex->pool.spin_grace_ms = std::max(0, atoi(e));
   ex->pool.start(ex->n_threads);
   *out = ex;
