@@ -164,7 +164,6 @@ PIPE_CASES = [
     # graph engine (lanes / group graphs / PDL)
     ("book", "adam", "fp32", "mailbox", 2, 1, False, False, {"engine": "graph"}),
     ("book", "adam", "fp32", "mailbox", 4, 2, True, False, {"engine": "graph"}),
-    ("book", "adam", "fp32", "mailbox", 4, 2, True, True, {"engine": "graph"}),   # head fused into the forward GEMM
     ("book", "sgd", "fp32", "atomic", 4, 4, True, False, {"engine": "graph"}),
     ("wide", "adam", "bf16", "mailbox", 4, 2, True),
     ("zhihu", "sgd", "fp32", "mailbox", 2, 2, False),
@@ -188,12 +187,12 @@ def check_pipelined(only=None) -> bool:
         (model, okind, dtype, push, lanes, gsteps, pdl), fuse = case[:7], (len(case) > 7 and case[7])
         extra = case[8] if len(case) > 8 else {}
         name = (f"pipelined model={model} opt={okind} dtype={dtype} push={push} lanes={lanes} graph_steps={gsteps} "
-                f"pdl={pdl} fuse_head={fuse} {extra or ''}")
+                f"pdl={pdl} {extra or ''}")
         try:
             spec = mlp.get_model(model)
             opt = OptimizerConfig(okind, 1e-3 if okind == "adam" else 1e-2)
             cfg = EngineConfig(backend="cuda", dtype=dtype, push_mode=push, lanes=lanes, graph_steps=gsteps,
-                               nslots=max(2, lanes), pipeline_slots=max(4, 2 * lanes), pdl=pdl, fuse_head=fuse,
+                               nslots=max(2, lanes), pipeline_slots=max(4, 2 * lanes), pdl=pdl,
                                engine=extra.get("engine", "auto"), sharding=extra.get("sharding", "round_robin"),
                                strict_steps=extra.get("strict_steps", False))
             with InProcessCluster(spec, opt, cfg, batch_size=32, num_ps=extra.get("num_ps", 1)) as cl:
@@ -211,10 +210,7 @@ def check_pipelined(only=None) -> bool:
                 seqs = sorted(o.seq for o in outs)
                 first = sum(o.loss for o in outs[:20]) / 20
                 last = sum(o.loss for o in outs[-20:]) / 20
-                if fuse:
-                    good_fused = w.kernels_per_step == 2   # the head really ran inside the forward kernel
-                else:
-                    good_fused = True
+                good_fused = True
                 good = (good_fused and len(outs) == total and gs == total and seqs == list(range(1, total + 1))
                         and last < first and all(o.loss == o.loss for o in outs))
                 print(f"[{'PASS' if good else 'FAIL'}] {name}: engine={w.engine} steps={len(outs)} global_step={gs} "

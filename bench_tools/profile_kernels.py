@@ -40,7 +40,6 @@ def main() -> int:
     ap.add_argument("--phases", action="store_true", help="print in-kernel phase timestamps of the GEMM kernels")
     ap.add_argument("--fwd_splits", type=int, default=None)
     ap.add_argument("--pdl", action="store_true", help="programmatic dependent launch for every kernel but the first")
-    ap.add_argument("--fuse_head", action="store_true", help="run the head as the tail of the forward GEMM (L == 2)")
     args = ap.parse_args()
     dev = "cuda"
     spec = mlp.get_model(args.model)
@@ -121,8 +120,6 @@ def main() -> int:
                                   item_base=wl.item_base, bn=lay.dw_tile_n, lddy=dact[l + 1].shape[1],
                                   ldx=ld_in if l == 0 else act[l].shape[1], ldw=wl.ld, name=f"dw{l}"))
 
-    if args.fuse_head and L == 2 and plans[0].can_fuse_head(sizes[L - 1][0], spec.num_classes):
-        plans[0].fuse_head(plans[1].params)
         plans[0].name = "fwd0+head"
         del plans[1]
     if args.pdl:

@@ -62,7 +62,7 @@ class GemmParams(C.Structure):
         ("splitk_counter", C.c_void_p),
         ("debug_ts", C.c_void_p),
         ("splitk_cluster", C.c_int), ("pdl", C.c_int),
-        ("fuse_head", C.c_int), ("pad3_", C.c_int),
+        ("pad2_", C.c_int), ("pad3_", C.c_int),
     ]
 
 
@@ -230,7 +230,6 @@ def _declare(l: C.CDLL) -> None:
         "dm_cpu_ps_applied": (u64, [vp]),
         "dm_cpu_ps_join": (i, [vp]),
         "dm_prepare_kernels": (i, [i]),
-        "dm_launch_gemm_head": (i, [vp, vp, vp, vp, i, i, i, i, vp]),
         "dm_exec_acquire_slot": (i, [vp, C.POINTER(i)]),
         "dm_exec_last_error": (C.c_char_p, []),
         "dm_loader_create": (vp, [vp, vp, sz, sz, sz, sz, sz, i, u64, i]),

@@ -17,8 +17,7 @@
 
 namespace dm {
 size_t gemm_smem_bytes(int bn, int stages, int cluster);
-cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, const HeadParams& hp,
-                        int dtype, bool a_mn,
+cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int dtype, bool a_mn,
                         bool b_mn, int splits, cudaStream_t stream);
 size_t head_smem_bytes(int B_pad, int H, int C);
 cudaError_t prepare_gemm_kernels();
@@ -282,24 +281,15 @@ int dm_fused_max_lanes(int dev, int* out) {
 }
 int dm_fused_smem_bytes() { return static_cast<int>(dm::fused_smem_bytes()); }
 
-// head_params: HeadParams of the fused classifier head (GemmParams::fuse_head), or null
-int dm_launch_gemm_head(const void* tmA, const void* tmB, const void* params, const void* head_params, int dtype,
-                        int a_mn, int b_mn, int splits, void* stream) {
+int dm_launch_gemm(const void* tmA, const void* tmB, const void* params, int dtype, int a_mn, int b_mn, int splits,
+                   void* stream) {
   CUtensorMap a, b;
   dm::GemmParams p;
-  dm::HeadParams hp;
   memcpy(&a, tmA, sizeof(a));
   memcpy(&b, tmB, sizeof(b));
   memcpy(&p, params, sizeof(p));
-  if (head_params != nullptr) memcpy(&hp, head_params, sizeof(hp));
-  else memset(&hp, 0, sizeof(hp));
-  if (head_params == nullptr && p.fuse_head) { g_err = "dm_launch_gemm: fuse_head without HeadParams"; return -1; }
-  DM_CUDA(dm::launch_gemm(a, b, p, hp, dtype, a_mn != 0, b_mn != 0, splits, static_cast<cudaStream_t>(stream)));
+  DM_CUDA(dm::launch_gemm(a, b, p, dtype, a_mn != 0, b_mn != 0, splits, static_cast<cudaStream_t>(stream)));
   return 0;
-}
-int dm_launch_gemm(const void* tmA, const void* tmB, const void* params, int dtype, int a_mn, int b_mn, int splits,
-                   void* stream) {
-  return dm_launch_gemm_head(tmA, tmB, params, nullptr, dtype, a_mn, b_mn, splits, stream);
 }
 int dm_launch_head(const void* params, void* stream) {
   dm::HeadParams p;

@@ -21,8 +21,7 @@
 // Split-K (forward / dX, whose K loop is TMA-issue bound on one SM): the splits of a tile form a thread-block
 // cluster and reduce-scatter their partial accumulators through distributed shared memory (global-scratch
 // variants remain for tiles wider than 64 columns). Kernels of one training step are chained with programmatic
-// dependent launch (griddepcontrol). Optional: the classifier head as the tail of the forward cluster
-// (fused_head_tail, GemmParams::fuse_head — correct, currently slower than the separate head kernel).
+// dependent launch (griddepcontrol). (The 784-H-10 models run the whole step in fused_step_sm100.cu instead.)
 #include "common.cuh"
 #include "protocol.h"
 
@@ -69,251 +68,12 @@ __device__ __forceinline__ void epilogue_colsum(const GemmParams& p, float colsu
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// Fused classifier head (GemmParams::fuse_head): the tail of the cluster split-K forward GEMM of the last hidden
-// layer. After the DSMEM reduce-scatter CTA r owns batch rows [r*cw, (r+1)*cw) of the activations for all <= 128
-// hidden units (one per epilogue thread), which is exactly what the head needs per row:
-//   logits / softmax / loss / accuracy / dlogits for my rows, dpre = (dlogits . W_last) * relu' for my rows,
-//   partial dW_last / db_hidden / db_last over my rows -> reduced to CTA 0 through distributed shared memory,
-//   which waits for the mailbox slot's ack, pushes the three small gradients and writes the step result.
-// Same math and protocol as head_kernel (head_sm100.cu), which remains the path for wider last hidden layers,
-// evaluation and non-cluster launches; one kernel launch and ~6 us less per step for the 784-H-10 models.
-// ------------------------------------------------------------------------------------------
-constexpr int kFhMaxC = 16;                 // classes (padded)
-constexpr int kFhMaxCw = 8;                 // batch rows per CTA (bn <= 64 with 8 CTAs)
-constexpr int kFhWlStride = kTileM + 4;     // smem row stride of W_last: 16 class rows land in distinct bank groups
-constexpr int kFhPart = 12;                 // floats per (src CTA, hidden unit): dW_last[0..9], pad, db_hidden
-struct FhSmem {                             // aliases the operand ring (free once the accumulator has been read)
-  float val[kFhMaxCw][kTileM];
-  float wl[kFhMaxC][kFhWlStride];
-  float dl[kFhMaxCw][kFhMaxC];
-  float red[8];
-  float part[8][kTileM][kFhPart];           // landing zone in CTA 0
-  float dbl[8][kFhMaxC];
-  float scal[8][2];
-};
-
-static_assert(sizeof(FhSmem) == 62816, "keep FUSED_HEAD_SMEM_BYTES in ops/gemm.py in sync");
-
-struct FhPush {
-  float* base;
-  uint32_t* flags;
-};
-__device__ __forceinline__ FhPush fh_resolve(const PushTarget& t, uint32_t seq) {
-  FhPush r{t.base, t.flags};
-  if (t.mode == PUSH_MAILBOX) {
-    const uint32_t slot = seq % t.nslots;
-    r.base = t.base + static_cast<uint64_t>(slot) * t.slot_stride;
-    r.flags = t.flags + static_cast<uint64_t>(slot) * t.flag_slot_stride;
-  }
-  return r;
-}
-__device__ __forceinline__ void fh_push(const PushTarget& t, float* dst, float v) {
-  if (t.mode == PUSH_ATOMIC) red_add_sys_f32(dst, t.scale * v);
-  else *dst = v;
-}
-
-// Called by every thread of every CTA of the cluster (it contains a cluster barrier). Epilogue threads (warp >= 2)
-// have stored the activations of their hidden unit for the CTA's rows in fs->val[row][unit] and pass their column
-// of W_last in wl[].
-__device__ __forceinline__ void fused_head_tail(const GemmParams& p, const HeadParams& hp, FhSmem* fs, const float* wl,
-                                                int warp, int lane, uint32_t crank, int cw, int n0, int m, bool m_ok,
-                                                uint32_t seq) {
-  const int C = hp.C, B = hp.B;
-  const bool epi = warp >= 2;
-  const int et = (warp & 3) * 32 + lane;     // epilogue thread index == tile row of this thread
-  float dw[kFhMaxC];
-  float dbh = 0.f;
-#pragma unroll
-  for (int c = 0; c < kFhMaxC; ++c) dw[c] = 0.f;
-  if (epi) {
-    // ---- my activations are in fs->val[.][et] already (written by the column-sum loop); stage my W_last column ----
-#pragma unroll
-    for (int c = 0; c < kFhMaxC; ++c) fs->wl[c][et] = wl[c];
-    named_bar_sync(1, 128);
-    // ---- logits, softmax, loss, accuracy, dlogits: thread -> (row rr, class c), 16 lanes per row ----
-    {
-      const int rr = et >> 4, c = et & (kFhMaxC - 1);
-      const bool c_ok = c < C;
-      const int n = n0 + static_cast<int>(crank) * cw + rr;
-      const bool row_ok = rr < cw && n < B;
-      const float y = (c_ok && row_ok) ? hp.labels[static_cast<size_t>(n) * C + c] : 0.f;
-      const float bias = c_ok ? hp.b_last[c] : 0.f;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      const float* hrow = fs->val[rr & (kFhMaxCw - 1)];
-      const float* wrow = fs->wl[c];
-#pragma unroll 8
-      for (int k = 0; k < kTileM; k += 4) {   // rows / columns beyond H are zero in both operands
-        const float4 hv = *reinterpret_cast<const float4*>(hrow + k);
-        const float4 wv = *reinterpret_cast<const float4*>(wrow + k);
-        a0 = fmaf(hv.x, wv.x, a0); a1 = fmaf(hv.y, wv.y, a1);
-        a2 = fmaf(hv.z, wv.z, a2); a3 = fmaf(hv.w, wv.w, a3);
-      }
-      const float z = c_ok ? (a0 + a1) + (a2 + a3) + bias : -INFINITY;
-      float zmax = z, ybest = c_ok ? y : -INFINITY, ysum = y;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-        zmax = fmaxf(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
-        ybest = fmaxf(ybest, __shfl_xor_sync(0xffffffffu, ybest, o));
-        ysum += __shfl_xor_sync(0xffffffffu, ysum, o);
-      }
-      int zarg = (c_ok && z == zmax) ? c : kFhMaxC, yarg = (c_ok && y == ybest) ? c : kFhMaxC;  // first maximum wins
-      const float e = c_ok ? __expf(z - zmax) : 0.f;
-      float esum = e;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-        zarg = min(zarg, __shfl_xor_sync(0xffffffffu, zarg, o));
-        yarg = min(yarg, __shfl_xor_sync(0xffffffffu, yarg, o));
-        esum += __shfl_xor_sync(0xffffffffu, esum, o);
-      }
-      const float pc = e / esum;
-      float dl = 0.f, lc = 0.f;
-      if (hp.loss_kind == LOSS_BOOK) {
-        const float k = 1.f / (static_cast<float>(B) * static_cast<float>(C));
-        const bool pass = c_ok && (pc >= 1e-10f) && (pc <= 1.0f);
-        const float g = pass ? (-k * y / pc) : 0.f;
-        float gp = g * pc;
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) gp += __shfl_xor_sync(0xffffffffu, gp, o);
-        dl = pc * (g - gp);
-        lc = c_ok ? -k * y * __logf(fminf(fmaxf(pc, 1e-10f), 1.0f)) : 0.f;
-      } else {
-        const float k = 1.f / static_cast<float>(B);
-        dl = k * (pc * ysum - y);
-        lc = c_ok ? -k * y * (z - (zmax + __logf(esum))) : 0.f;
-      }
-      float loss_part = 0.f, corr_part = 0.f;
-      if (row_ok) {
-        loss_part = lc;
-        corr_part = (c == 0 && zarg == yarg) ? 1.f : 0.f;
-      }
-      if (rr < kFhMaxCw) fs->dl[rr][c] = (row_ok && c_ok) ? dl : 0.f;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        loss_part += __shfl_xor_sync(0xffffffffu, loss_part, o);
-        corr_part += __shfl_xor_sync(0xffffffffu, corr_part, o);
-      }
-      if (lane == 0) { fs->red[warp & 3] = loss_part; fs->red[4 + (warp & 3)] = corr_part; }
-    }
-    named_bar_sync(1, 128);
-    // ---- gradients for my rows; thread -> hidden unit m ----
-    for (int rr = 0; rr < cw; ++rr) {
-      const int n = n0 + static_cast<int>(crank) * cw + rr;
-      const float hv = fs->val[rr][et];
-      float dh = 0.f;
-#pragma unroll
-      for (int c = 0; c < kFhMaxC; ++c) {
-        const float d = fs->dl[rr][c];          // broadcast read
-        dh = fmaf(d, wl[c], dh);
-        dw[c] = fmaf(d, hv, dw[c]);
-      }
-      const float dp = hv > 0.f ? dh : 0.f;
-      dbh += dp;
-      if (m_ok && n < hp.B_pad) {               // rows >= B carry zeros: the dW GEMM reduces over all B_pad rows
-        const size_t o = static_cast<size_t>(n) * hp.ldh + m;
-        if (hp.act_bf16) reinterpret_cast<__nv_bfloat16*>(hp.dpre)[o] = __float2bfloat16(dp);
-        else reinterpret_cast<float*>(hp.dpre)[o] = dp;
-      }
-    }
-    // ---- partial sums -> CTA 0 of the cluster ----
-    const uint32_t pbase = smem_u32(&fs->part[crank][et][0]);
-#pragma unroll
-    for (int c = 0; c < kFhPart - 1; ++c)
-      st_shared_cluster_f32(mapa_shared_cluster(pbase + static_cast<uint32_t>(c) * 4u, 0), c < kFhMaxC ? dw[c] : 0.f);
-    st_shared_cluster_f32(mapa_shared_cluster(pbase + static_cast<uint32_t>(kFhPart - 1) * 4u, 0), dbh);
-    if (et < kFhMaxC) {
-      float sdl = 0.f;
-      for (int rr = 0; rr < cw; ++rr) sdl += fs->dl[rr][et];
-      st_shared_cluster_f32(mapa_shared_cluster(smem_u32(&fs->dbl[crank][et]), 0), sdl);
-    }
-    if (et == 0) {
-      const float l = (fs->red[0] + fs->red[1]) + (fs->red[2] + fs->red[3]);
-      const float cr = (fs->red[4] + fs->red[5]) + (fs->red[6] + fs->red[7]);
-      st_shared_cluster_f32(mapa_shared_cluster(smem_u32(&fs->scal[crank][0]), 0), l);
-      st_shared_cluster_f32(mapa_shared_cluster(smem_u32(&fs->scal[crank][1]), 0), cr);
-    }
-  }
-  cluster_barrier_arrive_release();
-  cluster_barrier_wait_acquire();
-  if (crank != 0 || !epi) return;
-
-  // ---- CTA 0: total gradients, flow control, push, step result ----
-  const int nsplit = gridDim.z;
-  uint32_t gstep = seq;
-  if (et == 0) {
-    if (hp.compute_grads && hp.push.mode == PUSH_MAILBOX && hp.inbox != nullptr) {
-      // the mailbox slot we are about to overwrite was used by push (seq - nslots): wait for its ack
-      const volatile uint32_t* inbox = reinterpret_cast<const volatile uint32_t*>(hp.inbox);
-      if (seq > hp.nslots) {
-        const uint64_t t0 = globaltimer_ns();
-        for (uint32_t i = 0; i < hp.n_inbox; ++i) {
-          while (static_cast<int32_t>(inbox[2 * i] - (seq - hp.nslots)) < 0) {
-            if (globaltimer_ns() - t0 > DM_SPIN_TIMEOUT_NS) {
-              printf("[dm] fused head: PS %u ack timeout (seq=%u ack=%u)\n", i, seq, inbox[2 * i]);
-              __trap();
-            }
-          }
-        }
-      }
-      const uint32_t ack = inbox[0];
-      __threadfence();
-      gstep = inbox[1] + (seq - ack);
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < kFhMaxC; ++c) dw[c] = 0.f;
-  dbh = 0.f;
-  for (int src = 0; src < nsplit; ++src) {
-#pragma unroll
-    for (int c = 0; c < kFhPart - 1; ++c)
-      if (c < kFhMaxC) dw[c] += fs->part[src][et][c];
-    dbh += fs->part[src][et][kFhPart - 1];
-  }
-  named_bar_sync(1, 128);   // the ack wait of thread et == 0 precedes every store into the mailbox slot
-  const FhPush r = fh_resolve(hp.push, seq);
-  const FhPush rb = fh_resolve(hp.push_bh, seq);
-  const FhPush rl = fh_resolve(hp.push_bl, seq);
-  if (m_ok) {
-#pragma unroll
-    for (int c = 0; c < kFhPart - 1; ++c)
-      if (c < C) fh_push(hp.push, r.base + hp.off_w_last + static_cast<size_t>(c) * hp.H + m, dw[c]);
-    fh_push(hp.push_bh, rb.base + hp.off_b_hidden + m, dbh);
-  }
-  if (et < C) {
-    float s = 0.f;
-    for (int src = 0; src < nsplit; ++src) s += fs->dbl[src][et];
-    fh_push(hp.push_bl, rl.base + hp.off_b_last + et, s);
-  }
-  if (hp.push.mode == PUSH_MAILBOX) {
-    named_bar_sync(1, 128);   // every thread's P2P stores precede the one cumulative release below
-    if (et == 0) {
-      fence_acq_rel_scoped(hp.push.gpu_scope);
-      st_relaxed_sys_u32(r.flags + hp.item_w_last_base, seq);
-      st_relaxed_sys_u32(rb.flags + hp.item_b_hidden_base, seq);
-      st_relaxed_sys_u32(rl.flags + hp.item_b_last, seq);
-    }
-  }
-  if (et == 0) {
-    float l = 0.f, cr = 0.f;
-    for (int src = 0; src < nsplit; ++src) { l += fs->scal[src][0]; cr += fs->scal[src][1]; }
-    if (hp.push.mode == PUSH_ATOMIC && hp.ps_global_step != nullptr)
-      gstep = atom_add_sys_u32(hp.ps_global_step, 1u) + 1u;  // async SGD: this push *is* global step gstep
-    StepResult res;
-    res.loss = l;
-    res.global_step = gstep;
-    res.correct = static_cast<uint32_t>(cr + 0.5f);
-    res.seq = seq;
-    *hp.result = res;
-  }
-}
-
 template <typename T, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ GemmParams p, const __grid_constant__ HeadParams hp) {
+                    const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint32_t s_last;  // split-K: "this CTA arrived last at the tile counter"
-  __shared__ uint32_t s_seq_draw;  // the push sequence number this launch opened (CTA (0,0,0) only; fused head)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   constexpr int BKE = 128 / sizeof(T);     // k elements per stage chunk (32 tf32 / 64 bf16) == 128 bytes
@@ -374,7 +134,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (p.bump_seq != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
       const uint32_t sq = atomicAdd(p.seq_counter, 1u) + 1u;
       *p.bump_seq = sq;
-      s_seq_draw = sq;
     }
   }
   if (warp == 1) {
@@ -717,12 +476,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t crank = cluster_ctarank();
     const int cw = (bn + nsplit - 1) / nsplit;
     float colsum = 0.f;
-    constexpr bool kCanFuseHead = !A_MN && !B_MN;
-    const bool fuse_head = kCanFuseHead && p.fuse_head != 0;
-    float fh_wl[kFhMaxC];
-    FhSmem* fs = reinterpret_cast<FhSmem*>(smem);   // aliases the operand ring: every MMA of this CTA has completed
-    int fh_m = 0;
-    bool fh_mok = false;
     if (warp >= 2) {
       // ---- phase 2: sum the nsplit contributions of my columns and run the real epilogue on them ----
       const int q = warp & 3;
@@ -730,17 +483,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int m = m0 + mrow;
       const bool m_ok = m < p.M;
       const float bias = (p.bias != nullptr && m_ok) ? p.bias[m] : 0.f;
-      if constexpr (kCanFuseHead) {
-        fh_m = m;
-        fh_mok = m_ok;
-#pragma unroll
-        for (int c = 0; c < kFhMaxC; ++c)   // my column of W_last: peer loads, in flight during the column sums
-          fh_wl[c] = (fuse_head && m_ok && c < hp.C) ? hp.w_last[static_cast<size_t>(c) * hp.H + m] : 0.f;
-        if (fuse_head) {
-#pragma unroll
-          for (int rr = 0; rr < kFhMaxCw; ++rr) fs->val[rr][mrow] = 0.f;   // my hidden unit, the CTA's batch rows
-        }
-      }
       for (int cc = 0; cc < cw; ++cc) {
         const int c = static_cast<int>(crank) * cw + cc;
         if (c >= bn) break;
@@ -761,10 +503,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const size_t o = static_cast<size_t>(n) * p.ldo + m;
           if (p.out_bf16) reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(val);
           else reinterpret_cast<float*>(p.out)[o] = val;
-          if constexpr (kCanFuseHead) {
-            if (fuse_head && cc < kFhMaxCw)   // the head sees what a later kernel would read back from `out`
-              fs->val[cc][mrow] = p.out_bf16 ? __bfloat162float(__float2bfloat16(val)) : val;
-          }
         }
       }
       if (p.has_colsum) {
@@ -782,10 +520,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int src = 0; src < nsplit; ++src) tot += csum[src * kTileM + mrow];
         epilogue_colsum(p, tot, m0 + mrow, m0 + mrow < p.M);
       }
-    }
-    if constexpr (kCanFuseHead) {
-      if (fuse_head)   // uniform over the cluster: contains a cluster barrier
-        fused_head_tail(p, hp, fs, fh_wl, warp, lane, crank, cw, n0, fh_m, fh_mok, s_seq_draw);
     }
   }
 
@@ -834,24 +568,14 @@ cudaError_t prepare_gemm_kernels() {
 }
 
 template <typename T, bool A_MN, bool B_MN>
-static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
-                              const HeadParams& hp, dim3 grid, cudaStream_t stream) {
+static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, dim3 grid,
+                              cudaStream_t stream) {
   auto kern = gemm_tcgen05_kernel<T, A_MN, B_MN>;
   const bool cluster = p.splitk_cluster != 0 && grid.z > 1;
   const size_t smem = gemm_smem_bytes(p.bn, p.stages, cluster ? 1 : 0);
   if (smem > static_cast<size_t>(kMaxDynSmem)) return cudaErrorInvalidValue;
-  if (p.fuse_head) {
-    // fused head: forward GEMM, one M tile, cluster split-K whose CTAs own <= kFhMaxCw batch rows each, the head
-    // scratch fits into the operand ring, and this launch opens the push sequence number itself
-    const size_t ring = static_cast<size_t>(p.stages) * (kABytes + p.bn * 128);
-    const int cw = (p.bn + static_cast<int>(grid.z) - 1) / static_cast<int>(grid.z);
-    if (A_MN || B_MN || !cluster || grid.x != 1 || grid.y != 1 || p.epi != EPI_TRANSPOSED || cw > kFhMaxCw ||
-        sizeof(FhSmem) > ring || hp.C > kFhMaxC - 0 || hp.C > kFhPart - 1 || hp.H != p.M || hp.H > kTileM ||
-        p.bump_seq == nullptr || !hp.compute_grads || hp.result == nullptr)
-      return cudaErrorInvalidValue;
-  }
   if (!cluster && !p.pdl) {
-    kern<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p, hp);
+    kern<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p);
     return cudaGetLastError();
   }
   if (cluster && (grid.z > 8 || (2 * p.stages + 1) * sizeof(uint64_t) + 16 > 256)) return cudaErrorInvalidValue;
@@ -876,18 +600,18 @@ static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, co
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p, hp);
+  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
 }
 
 // dtype: 0 = fp32 (tf32 MMA), 1 = bf16
-cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, const HeadParams& hp,
-                        int dtype, bool a_mn, bool b_mn, int splits, cudaStream_t stream) {
+cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int dtype, bool a_mn,
+                        bool b_mn, int splits, cudaStream_t stream) {
   dim3 grid((p.M + kTileM - 1) / kTileM, (p.N + p.bn - 1) / p.bn, splits);
 #define DM_DISPATCH(T)                                                                  \
-  if (!a_mn && !b_mn) return launch_one<T, false, false>(tmA, tmB, p, hp, grid, stream);   \
-  if (a_mn && b_mn) return launch_one<T, true, true>(tmA, tmB, p, hp, grid, stream);       \
-  if (a_mn && !b_mn) return launch_one<T, true, false>(tmA, tmB, p, hp, grid, stream);     \
-  return launch_one<T, false, true>(tmA, tmB, p, hp, grid, stream);
+  if (!a_mn && !b_mn) return launch_one<T, false, false>(tmA, tmB, p, grid, stream);   \
+  if (a_mn && b_mn) return launch_one<T, true, true>(tmA, tmB, p, grid, stream);       \
+  if (a_mn && !b_mn) return launch_one<T, true, false>(tmA, tmB, p, grid, stream);     \
+  return launch_one<T, false, true>(tmA, tmB, p, grid, stream);
   if (dtype == 0) {
     DM_DISPATCH(float)
   } else {

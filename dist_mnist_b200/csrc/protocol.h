@@ -81,9 +81,7 @@ struct GemmParams {
   int pdl;                   //    their partial accumulators through distributed shared memory
                              // pdl = 1: launch with programmatic stream serialization (prologue overlaps the
                              //    previous kernel of the step; data reads wait on griddepcontrol.wait)
-  int fuse_head;             // 1: forward GEMM of the last hidden layer, cluster split-K: after the reduce-scatter
-  int pad3_;                 //    every CTA runs the classifier head (HeadParams, 4th kernel argument) on the batch
-                             //    rows it owns; partial dW_last / db are reduced to CTA 0 through DSMEM and pushed
+  int pad2_, pad3_;
 };
 
 // Softmax-cross-entropy head (last dense layer + loss + its gradients), see head_sm100.cu

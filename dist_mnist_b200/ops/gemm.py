@@ -74,42 +74,21 @@ class GemmPlan:
     name: str = "gemm"
     scratch: object = None    # split-K partial tiles (kept alive with the plan)
     counters: object = None
-    head_params: object = None   # N.HeadParams of the fused classifier head (params.fuse_head == 1)
 
     def launch(self, stream: Optional[int] = None) -> None:
         s = N.current_stream_ptr() if stream is None else stream
         N.ensure_prepared()
-        hp = C.addressof(self.head_params) if self.head_params is not None else None
         N.check(
-            N.lib().dm_launch_gemm_head(
-                C.addressof(self.tm_a), C.addressof(self.tm_b), C.addressof(self.params), hp, self.dtype,
+            N.lib().dm_launch_gemm(
+                C.addressof(self.tm_a), C.addressof(self.tm_b), C.addressof(self.params), self.dtype,
                 int(self.a_mn), int(self.b_mn), self.splits, s,
             ),
             f"launch {self.name}",
         )
 
-    def can_fuse_head(self, H: int, num_classes: int) -> bool:
-        """The classifier head can run as the tail of this forward GEMM (csrc/gemm_sm100.cu, fused_head_tail): one M
-        tile, cluster split-K whose CTAs own <= 8 batch rows each, <= 11 classes, operand ring >= head scratch."""
-        p = self.params
-        if not (p.splitk_cluster and self.splits > 1 and not self.a_mn and not self.b_mn and self.grid[0] == 1):
-            return False
-        cw = ceil_div(p.bn, self.splits)
-        ring = p.stages * (TILE_M * 128 + p.bn * 128)
-        return H == p.M and H <= TILE_M and cw <= 8 and num_classes <= 11 and ring >= FUSED_HEAD_SMEM_BYTES
-
-    def fuse_head(self, head_params) -> None:
-        self.head_params = head_params
-        self.params.fuse_head = 1
-
     @property
     def smem_bytes(self) -> int:
         return N.lib().dm_gemm_smem_bytes(self.params.bn, self.params.stages, int(self.params.splitk_cluster))
-
-
-# sizeof(FhSmem) in csrc/gemm_sm100.cu: val[8][128] + wl[16][132] + dl[8][16] + red[8] + part[8][128][12] + dbl[8][16]
-# + scal[8][2] floats
-FUSED_HEAD_SMEM_BYTES = 4 * (8 * 128 + 16 * 132 + 8 * 16 + 8 + 8 * 128 * 12 + 8 * 16 + 8 * 2)
 
 
 def _pick_stages(bn: int, kc: int) -> int:

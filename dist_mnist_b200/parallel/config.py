@@ -62,8 +62,6 @@ class EngineConfig:
     graph_steps: int = 1             # steps per CUDA-graph launch in the native loops (U parallel step chains in
                                      # one graph: one input transfer + one launch per U steps); divides lanes
     pdl: bool = _env_flag("DM_PDL", True)   # programmatic dependent launch between the kernels of a step graph
-    fuse_head: bool = _env_flag("DM_FUSED_HEAD", False)   # single-hidden-layer models: run the classifier head as
-                                     # the tail of the forward GEMM's cluster (2 kernels per step instead of 3)
     colocate: bool = False           # worker i shares GPU i with ps i (N workers on N GPUs)
 
     @property

@@ -528,10 +528,7 @@ class Worker:
                 item_w_last_base=wl.item_base, item_b_last=bl.item_base, item_b_hidden_base=hb.item_base,
                 seq_ptr=seq_ptr, inbox_ptr=inbox_ptr, n_inbox=len(self.inbox_order), ps_global_step_ptr=gs_ptr,
                 nslots=cfg.nslots, ldh=act[L - 1].shape[1])
-            if cfg.fuse_head and L == 2 and plans[0].can_fuse_head(sizes[L - 1][0], spec.num_classes):
-                plans[0].fuse_head(head.params)      # the head runs as the tail of the forward GEMM's cluster
-            else:
-                plans.append(head)
+            plans.append(head)
             # ---- backward of the hidden layers: dX (+ bias-grad push) *before* dW (fused push) of the same layer:
             #      dX pulls W_l from the PS a second time, and the PS applies a pushed dW_l within microseconds,
             #      so pushing dW_l first would let this step's own update leak into its dX ----
