@@ -71,6 +71,7 @@ def main() -> int:
     local_buf = torch.empty(args.max_bytes, dtype=torch.uint8, device="cuda")
     local_buf.random_(0, 255)
     nccl_buf = torch.empty(args.max_bytes // 4, dtype=torch.float32, device="cuda")
+    host_buf = torch.empty(args.max_bytes, dtype=torch.uint8).pin_memory() if rank > 0 else None
     stream = N.current_stream_ptr()
     results = []
     size = args.min_bytes
@@ -110,6 +111,23 @@ def main() -> int:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         row["nccl_broadcast_s"] = float(tt)
         row["nccl_broadcast_GBps_per_worker"] = size / float(tt) / 1e9
+        # Host-staged STAND-IN for the reference's gRPC data path (tf.train.Server, DS:80): the bytes leave the worker
+        # GPU into pinned host memory and enter a GPU again — the two PCIe hops every gRPC tensor transfer makes —
+        # WITHOUT any TCP, protobuf serialisation or host copy: an optimistic bound, labelled as a stand-in.
+        t = 0.0
+        if rank > 0:
+            hv, dv = host_buf[:size], local_buf[:size]
+            def staged():
+                hv.copy_(dv, non_blocking=True)
+                dv.copy_(hv, non_blocking=True)
+            dist.barrier()
+            t = time_op(staged, max(2, iters // 2))
+        else:
+            dist.barrier()
+        tt = torch.tensor([t], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        row["host_staged_standin_s"] = float(tt)
+        row["host_staged_standin_GBps_per_worker"] = size / float(tt) / 1e9
         results.append(row)
         if rank == 0:
             print(json.dumps(row), flush=True)
