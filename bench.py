@@ -79,7 +79,8 @@ def engine_config(args, backend: str = "cuda"):
     lanes = max(1, args.lanes)
     return EngineConfig(backend=backend, dtype=args.dtype, nslots=args.nslots or max(4 * lanes, 8), apply_mode=args.apply_mode,
                         push_mode=args.push_mode, sharding=args.sharding, lanes=lanes,
-                        graph_steps=args.graph_steps or min(lanes, 4), pipeline_slots=max(4, 2 * lanes),
+                        graph_steps=args.graph_steps or next(u for u in (4, 3, 2, 1) if lanes % u == 0),
+                        pipeline_slots=max(4, 2 * lanes),
                         engine=args.engine, strict_steps=args.strict_steps, ps_row_blocks=args.ps_row_blocks)
 
 

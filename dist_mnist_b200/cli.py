@@ -42,7 +42,7 @@ def engine_config_from_args(args, backend: str) -> EngineConfig:
     """The engine configuration every task derives from the command line (ps and worker tasks must agree)."""
     lanes = max(1, args.lanes)
     nslots = args.nslots or max(4 * lanes, 8)
-    gsteps = args.graph_steps or min(lanes, 4)
+    gsteps = args.graph_steps or next(u for u in (4, 3, 2, 1) if lanes % u == 0)   # largest divisor of lanes <= 4
     return EngineConfig(backend=backend, dtype=args.dtype, nslots=nslots, apply_mode=args.apply_mode,
                         push_mode=args.push_mode, sharding=args.sharding, colocate=args.colocate, lanes=lanes,
                         graph_steps=gsteps, pipeline_slots=max(4, 2 * lanes), engine=args.engine,
