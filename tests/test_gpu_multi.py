@@ -65,3 +65,32 @@ def test_bench_two_gpus_contract():
     assert d["gpu_launches"] >= 1 and d["gpu_launches"] * d["steps_per_launch"] >= 300
     assert d["config"]["global_step_after_run"] >= 300 and d["config"]["engine"] == "fused"
     assert d["parity"]["value_device_timed"] > 0
+
+
+def _local_steps(out):
+    import re
+    m = re.search(r"local_steps=(\d+)", out)
+    assert m, out
+    return int(m.group(1))
+
+
+@pytest.mark.parametrize("n_ps,extra", [(1, []), (2, ["--sharding", "row_split"])])
+def test_documented_topology_one_process_per_gpu(n_ps, extra):
+    """The reference's README topology (1 ps + 2 workers, /root/reference/README.md:7-9) with every task on its own
+    GPU (3 GPUs; 4 with two row-split ps shards): the shared step counter equals the number of pushes."""
+    import re
+    _need_gpus(n_ps + 2)
+    ps_hosts = ",".join(f"127.0.0.1:{_free_port()}" for _ in range(n_ps))
+    worker_hosts = f"127.0.0.1:{_free_port()},127.0.0.1:{_free_port()}"
+    common = ["--train_steps", "2000", "--learning_rate", "0.001", "--log_every", "500", *extra]
+    pss = [_spawn("ps", k, ps_hosts, worker_hosts, common + ["--ps_exit_when_done"]) for k in range(n_ps)]
+    ws = [_spawn("worker", i, ps_hosts, worker_hosts, common) for i in range(2)]
+    outs_w = [w.communicate(timeout=300)[0] for w in ws]
+    outs_p = [p.communicate(timeout=90)[0] for p in pss]
+    for w, o in zip(ws, outs_w):
+        assert w.returncode == 0 and "engine=fused" in o, o
+    for p, o in zip(pss, outs_p):
+        assert p.returncode == 0, o
+    total = sum(_local_steps(o) for o in outs_w)
+    owner = [int(m.group(1)) for o in outs_p for m in [re.search(r"global_step=(\d+) owns_global_step=1", o)] if m]
+    assert owner and owner[0] == total >= 2000, (owner, total, outs_p)
