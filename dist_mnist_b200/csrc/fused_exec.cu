@@ -392,7 +392,6 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
   ex->pool.cv.notify_all();
   uint64_t total_done = 0;
   bool stop = false;
-  bool first_launch = true;
   size_t next_gather = 0, next_launch = 0, next_harvest = 0;
   int rc = 0;
   auto harvest = [&](size_t c, bool wait) -> int {   // 1 = harvested, 0 = not ready, -1 = error
@@ -482,7 +481,6 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
       ex->steps_done = saved;
       if (lrc != 0) { rc = -1; break; }
       if (trace) fprintf(stderr, "[fexec] chunk %zu (%u steps) launched at +%.1f us\n", c, b.n, us_since());
-      first_launch = false;
       e = cudaEventRecord(b.done, ex->compute);
       if (e != cudaSuccess) { rc = fxfail("cudaEventRecord", e); break; }
       ++next_launch;

@@ -68,3 +68,38 @@ def test_native_loader_visits_every_sample_once_per_epoch(n, batch, n_batches, s
         assert order == [i % n for i in range(total)]
     assert lib.dm_loader_epochs(h) == (total - 1) // n     # the wrap happens lazily, when the next sample is needed
     lib.dm_loader_destroy(h)
+
+
+@settings(max_examples=40, deadline=None)
+@given(in_chunks=st.integers(8, 32), in_tail=st.sampled_from([0, 4, 8, 16, 28]), hidden=st.integers(1, 128),
+       classes=st.integers(2, 11), num_ps=st.integers(1, 8),
+       strategy=st.sampled_from(["round_robin", "byte_balanced", "row_split"]), row_blocks=st.integers(1, 8))
+def test_fused_tiling_any_eligible_model(in_chunks, in_tail, hidden, classes, num_ps, strategy, row_blocks):
+    """Fused step engine tiling for any eligible 1-hidden-layer model: 8 K-slices (<= 4 chunks each) cover the input
+    features exactly, every parameter belongs to exactly one ps item, every item's flag exists on its shard, rows of
+    the hidden weight are whole 128-byte lines, and with row_split the slices are dealt round-robin over the shards."""
+    in_features = (in_chunks - 1) * 32 + (in_tail if in_tail else 32)
+    spec = MLPSpec(name="book", in_features=in_features, hidden=(hidden,), num_classes=classes, loss="book", init="book")
+    assert sharding.fused_eligible(spec, 32)
+    lay = sharding.build_layout(spec, num_ps, strategy, dw_tile_n=32, engine="fused", ps_row_blocks=row_blocks)
+    sl = lay.fused_slices
+    assert [s.rank for s in sl] == list(range(8))
+    assert sl[0].kc_begin == 0 and all(a.kc_begin + max(a.kc_count, 0) <= b.kc_begin or a.kc_count == 0
+                                       for a, b in zip(sl, sl[1:]))
+    assert sum(s.kc_count for s in sl) == in_chunks and max(s.kc_count for s in sl) <= 4
+    hw = lay.by_name["hid_w"]
+    assert hw.ld % 32 == 0 and hw.ld >= in_features
+    total = 0
+    for sh in lay.shards:
+        cover = torch.zeros(sh.arena_elems, dtype=torch.int32)
+        for it in sh.items:
+            assert 0 <= it.flag < sh.n_flags
+            for r in range(it.rows):
+                cover[it.offset + r * it.ld: it.offset + r * it.ld + it.cols] += 1
+        assert int(cover.max()) <= 1
+        total += int(cover.sum())
+    assert total == spec.num_params
+    if strategy == "row_split":
+        assert [s.ps for s in sl] == [r % num_ps for r in range(8)]
+    else:
+        assert len({s.ps for s in sl}) == 1
