@@ -14,9 +14,11 @@ Numbers in the JSON line (all: max over ranks, throughput = workers x K / max el
              fused engine ONE kernel launch whose TMA loads take the batch rows straight out of the dataset —
              timed with CUDA events on the worker's compute stream; the region ends with a stream-ordered wait for
              the ps acknowledgement of the last push, so every step's pull, math, push and optimizer apply is inside.
-  e2e      : the same K steps through the public API (`Worker.run_steps`): native next_batch gather into pinned
-             memory, H2D copy of every batch, step kernels, 16-byte result read back per step; wall clock between
-             device synchronisations, closed by the ps acknowledgement of the last push.
+  e2e      : the same K steps through the public API (`Worker.run_steps`): native next_batch out of the loader's
+             epoch-shuffled pinned buffer (TF DataSet semantics: rows are shuffled physically once per epoch — here by
+             background threads — and a batch is a contiguous slice), H2D copy of every batch from that pinned memory,
+             step kernels, 16-byte result read back per step; wall clock between device synchronisations, closed by the
+             ps acknowledgement of the last push. `input_feed` in the e2e object says which path fed the timed steps.
   parity   : the reference's worker semantics — one step at a time per worker (`--lanes 1`), host-fed — and the same
              with `--strict_steps` (the next pull waits for the acknowledgement of the previous push).
   roofline : achieved fraction of the NVLink / HBM / tensor-core rooflines from MEASURED_PEAKS.json.
@@ -294,6 +296,7 @@ def main(argv=None) -> int:
     par = {"dev_ms": 0.0, "e2e_s": 0.0, "strict_ms": 0.0}
     h2d_bytes = d2h_bytes = 0
     launches = 0
+    feed_delta = {"direct_chunks": 0, "gathered_chunks": 0, "fills_posted": 0}
     # clocks are sampled from here to the end of the last timed region (started before the warm-up: nvidia-smi's own
     # start-up takes tens of milliseconds and contends for driver locks, which must not sit between the barrier and
     # the first timed launch)
@@ -324,7 +327,10 @@ def main(argv=None) -> int:
             worker.run_steps(W, loaders["l"])
         full_sync()
         if worker is not None:
+            feed_before = worker.feed_stats()
             e2e_s = host_fed(K)
+            feed_after = worker.feed_stats()
+            feed_delta = {k: feed_after[k] - feed_before[k] for k in feed_after}
             h2d_bytes = worker.x_bytes + worker.y_bytes
             d2h_bytes = C.sizeof(N.StepResult)
         full_sync()
@@ -366,7 +372,8 @@ def main(argv=None) -> int:
     # ---------------- reduce over ranks ----------------
     kps = worker.kernels_per_step if worker is not None else 0
     stats = torch.tensor([elapsed_ms, e2e_s, float(launches), float(h2d_bytes), float(d2h_bytes), float(final_step),
-                          float(kps), host_enqueue_ms, par["dev_ms"], par["e2e_s"], par["strict_ms"]],
+                          float(kps), host_enqueue_ms, par["dev_ms"], par["e2e_s"], par["strict_ms"],
+                          float(feed_delta["direct_chunks"]), float(feed_delta["gathered_chunks"])],
                          dtype=torch.float64, device="cuda")
     mx = stats.clone()
     sm = stats.clone()
@@ -439,6 +446,13 @@ def main(argv=None) -> int:
             "impl": "ours",
         }
         if not args.skip_e2e:
+            # summed over the workers: how the timed e2e steps got their inputs
+            feed_desc = {
+                "chunks_from_epoch_buffer": int(sm[11]), "chunks_row_gathered": int(sm[12]),
+                "what": "pinned epoch-shuffled dataset buffer -> one contiguous H2D copy per chunk of steps (TF DataSet "
+                        "semantics; the next epoch is shuffled into a second pinned buffer by background threads); "
+                        "row-gathered chunks go dataset -> pinned staging -> H2D",
+            }
             out["e2e"] = {
                 "value": n_workers * K / max_e2e,
                 "unit": "steps/s",
@@ -446,6 +460,7 @@ def main(argv=None) -> int:
                 "h2d_bytes_per_step": int(mx[3]),
                 "d2h_bytes_per_step": int(mx[4]),
                 "timing": "wall clock between device synchronisations, max over ranks",
+                "input_feed": feed_desc,
             }
         if do_parity:
             out["parity"] = {

@@ -23,8 +23,8 @@ LIB_NAME = "libdmnist_sm100a.so"
 LIB_PATH = PKG_DIR / LIB_NAME
 
 CUDA_SOURCES = ["gemm_sm100.cu", "head_sm100.cu", "ps_apply_sm100.cu", "p2p_sm100.cu", "fused_step_sm100.cu",
-                "executor.cu", "fused_exec.cu", "api.cu"]
-CXX_SOURCES = ["host_runtime.cpp"]
+                "nvls_sm100.cu", "executor.cu", "fused_exec.cu", "api.cu"]
+CXX_SOURCES = ["host_runtime.cpp", "loader_api.cpp"]
 HEADERS = ["common.cuh", "protocol.h", "fused.h", "loader.h"]
 
 NVCC_FLAGS = [

@@ -236,6 +236,8 @@ def _declare(l: C.CDLL) -> None:
         "dm_loader_next": (None, [vp, vp, vp]),
         "dm_loader_epochs": (u64, [vp]),
         "dm_loader_destroy": (None, [vp]),
+        "dm_loader_enable_feed": (i, [vp, vp, vp, vp, vp, i]),
+        "dm_loader_feed_enabled": (i, [vp]),
         "dm_exec_create": (i, [i, i, i, i, sz, sz, C.POINTER(vp)]),
         "dm_exec_capture_stream": (vp, [vp, i]),
         "dm_exec_graph_steps": (i, [vp]),
@@ -261,8 +263,10 @@ def _declare(l: C.CDLL) -> None:
         "dm_launch_fused": (i, [vp, vp, i, vp]),
         "dm_fused_max_lanes": (i, [i, C.POINTER(i)]),
         "dm_fused_smem_bytes": (i, []),
+        "dm_nvls_probe": (i, [i, sz, i, C.c_char_p, sz]),
         "dm_fexec_last_error": (C.c_char_p, []),
         "dm_fexec_create": (i, [i, i, i, i, i, C.POINTER(vp)]),
+        "dm_fexec_feed_stats": (None, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
         "dm_fexec_buffers": (i, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
                                  C.POINTER(i)]),
         "dm_fexec_set_params": (i, [vp, vp, vp]),
@@ -383,3 +387,12 @@ def make_tensor_map(ptr: int, dtype: int, dim0: int, dim1: int, stride1_bytes: i
         "cuTensorMapEncodeTiled",
     )
     return buf
+
+
+def nvls_probe(n_dev: int, nbytes: int, iters: int = 50) -> tuple[bool, str]:
+    """NVSwitch multicast probe (csrc/nvls_sm100.cu): builds a multicast team over the first ``n_dev`` GPUs of this
+    process, publishes ``nbytes`` from GPU 0 with ``multimem.st``, aggregates with ``multimem.ld_reduce`` and times both
+    against unicast peer stores / loads. Returns ``(ok, log)``; never raises on a box without GPUs or NVLS."""
+    buf = C.create_string_buffer(1 << 16)
+    rc = lib().dm_nvls_probe(int(n_dev), int(nbytes), int(iters), buf, len(buf))
+    return rc == 0, buf.value.decode(errors="replace")

@@ -107,33 +107,6 @@ extern "C" {
 const char* dm_exec_last_error() { return g_exec_err.c_str(); }
 
 // ---------------------------------------------------------------------------------------------
-// batch loader
-// ---------------------------------------------------------------------------------------------
-void* dm_loader_create(const void* images, const void* labels, size_t n, size_t x_row_bytes, size_t y_row_bytes,
-                       size_t x_dst_stride, size_t y_dst_stride, int batch, uint64_t seed, int shuffle) {
-  BatchLoader* l = new BatchLoader();
-  l->images = static_cast<const uint8_t*>(images);
-  l->labels = static_cast<const uint8_t*>(labels);
-  l->n = n;
-  l->x_row_bytes = x_row_bytes;
-  l->y_row_bytes = y_row_bytes;
-  l->x_dst_stride = x_dst_stride;
-  l->y_dst_stride = y_dst_stride;
-  l->batch = batch;
-  l->shuffle = shuffle != 0;
-  l->rng.seed(seed);
-  l->perm.resize(n);
-  for (size_t i = 0; i < n; ++i) l->perm[i] = static_cast<uint32_t>(i);
-  l->reshuffle();
-  return l;
-}
-void dm_loader_next(void* h, void* x_dst, void* y_dst) {
-  static_cast<BatchLoader*>(h)->next(static_cast<uint8_t*>(x_dst), static_cast<uint8_t*>(y_dst));
-}
-uint64_t dm_loader_epochs(void* h) { return static_cast<BatchLoader*>(h)->epochs; }
-void dm_loader_destroy(void* h) { delete static_cast<BatchLoader*>(h); }
-
-// ---------------------------------------------------------------------------------------------
 // executor
 // ---------------------------------------------------------------------------------------------
 // nslots: ring depth (steps); lanes: steps in flight on the GPU at once; graph_steps (U): steps per graph launch

@@ -11,6 +11,12 @@
 //                its x rows + one of its labels into a device ring buffer (copy stream) -> event -> one launch of
 //                the fused kernel for the chunk's steps (compute stream). Four chunk buffers rotate, so the gather
 //                and the transfer of chunk c+1 overlap the kernel of chunk c.
+//   epoch feed   with a loader whose epoch feed is enabled (loader.h) no row is gathered on the training thread at all:
+//                the current epoch's rows sit in permutation order in a pinned buffer, so a chunk that does not
+//                straddle an epoch boundary is ONE contiguous H2D copy straight out of that buffer, issued as soon
+//                as the chunk's ring buffer is free. The helper threads fill the next epoch's buffer in the
+//                background (low priority: they serve gather tasks first); only the chunk that contains the boundary
+//                goes through the gather path above.
 //   results      every step's {loss, global_step, correct, seq} is written by the kernel straight into pinned host
 //                memory (posted PCIe write); a chunk's results are valid once its completion event has fired.
 //   resident     `run_resident`: one launch for any number of steps over a device-resident dataset (the kernel's TMA
@@ -71,11 +77,26 @@ struct GatherTask {
   std::atomic<uint32_t>* done;  // += rows copied
 };
 
+// Background job: materialise one epoch of the loader's epoch feed (rows idx[0..n) of the dataset, in that order, into
+// x_dst / y_dst). Threads claim blocks of kFillBlock rows; between blocks they go back to the gather queue first.
+constexpr uint32_t kFillBlock = 64;
+struct FillJob {
+  const dm::BatchLoader* loader;
+  std::shared_ptr<std::vector<uint32_t>> idx;
+  uint8_t* x_dst;
+  uint8_t* y_dst;
+  uint32_t n;
+  std::atomic<uint32_t> next{0};   // first unclaimed row
+  std::atomic<uint32_t>* done;     // += rows copied (BatchLoader::feed_rows[b])
+};
+
 struct GatherPool {
   std::vector<std::thread> threads;
   std::mutex mu;
   std::condition_variable cv;
   std::deque<GatherTask*> queue;
+  std::deque<std::shared_ptr<FillJob>> fills;
+  std::atomic<bool> fill_active{false};
   std::atomic<int> active{0};     // > 0 while some run is in progress: workers spin instead of sleeping
   std::atomic<uint64_t> posted{0}, taken{0};
   bool quit = false;
@@ -110,6 +131,36 @@ struct GatherPool {
     }
     cv.notify_one();
   }
+  void post_fill(std::shared_ptr<FillJob> j) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      fills.push_back(std::move(j));
+      fill_active.store(true, std::memory_order_release);
+    }
+    cv.notify_all();
+  }
+  // One block of the oldest fill job; false when there is no fill work. Any thread may call it (the training thread
+  // does while it waits for an epoch buffer).
+  bool fill_step() {
+    if (!fill_active.load(std::memory_order_acquire)) return false;
+    std::shared_ptr<FillJob> j;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (fills.empty()) { fill_active.store(false, std::memory_order_release); return false; }
+      j = fills.front();
+    }
+    const uint32_t r0 = j->next.fetch_add(kFillBlock, std::memory_order_relaxed);
+    if (r0 >= j->n) {   // every block is claimed (some may still be in flight on other threads): retire the job
+      std::lock_guard<std::mutex> lk(mu);
+      if (!fills.empty() && fills.front() == j) fills.pop_front();
+      if (fills.empty()) fill_active.store(false, std::memory_order_release);
+      return true;
+    }
+    const uint32_t r1 = std::min(j->n, r0 + kFillBlock);
+    j->loader->copy_rows(j->idx->data(), static_cast<int>(r0), static_cast<int>(r1), j->x_dst, j->y_dst);
+    j->done->fetch_add(r1 - r0, std::memory_order_release);
+    return true;
+  }
   static void run_task(GatherTask* t) {
     t->loader->copy_rows(t->idx->data(), t->r0, t->r1, t->x_dst, t->y_dst);
     std::atomic<uint32_t>* d = t->done;
@@ -125,11 +176,12 @@ struct GatherPool {
     for (;;) {
       GatherTask* t = try_pop();
       if (t != nullptr) { run_task(t); last_active = std::chrono::steady_clock::now(); continue; }
+      if (fill_step()) { last_active = std::chrono::steady_clock::now(); continue; }
       if (active.load(std::memory_order_acquire) > 0) { cpu_relax(); last_active = std::chrono::steady_clock::now(); continue; }
       if (std::chrono::steady_clock::now() - last_active < std::chrono::milliseconds(spin_grace_ms)) { cpu_relax(); continue; }
       std::unique_lock<std::mutex> lk(mu);
-      cv.wait(lk, [this] { return quit || !queue.empty() || active.load(std::memory_order_acquire) > 0; });
-      if (quit && queue.empty()) return;
+      cv.wait(lk, [this] { return quit || !queue.empty() || !fills.empty() || active.load(std::memory_order_acquire) > 0; });
+      if (quit && queue.empty() && fills.empty()) return;   // posted work is always finished, also during shutdown
       last_active = std::chrono::steady_clock::now();
     }
   }
@@ -145,6 +197,7 @@ struct ChunkBuf {
   std::atomic<uint32_t> gathered{0};
   uint32_t n = 0;              // steps of the chunk currently occupying the buffer
   bool in_flight = false;
+  bool direct = false;         // fed straight from the loader's epoch buffer: its H2D copies are already enqueued
   uint64_t first_step = 0;     // index (within the run) of the chunk's first step
 };
 
@@ -167,6 +220,7 @@ struct FusedExec {
   bool warmed = false;
   uint64_t steps_done = 0;    // steps completed over the executor's lifetime == push sequence numbers used
   uint64_t launches = 0;
+  uint64_t direct_chunks = 0, gathered_chunks = 0, fills_posted = 0;   // feed statistics (dm_fexec_feed_stats)
   ChunkBuf bufs[kBuffers];
   GatherPool pool;
   cudaEvent_t t_start = nullptr, t_stop = nullptr;   // timing events of a timed resident launch
@@ -206,6 +260,34 @@ struct FusedExec {
     return 0;
   }
 };
+
+// Epoch feed: start materialising epoch `epochs + 1` into its buffer once that buffer is free — the fill of the epoch
+// that used it before has completed and no H2D copy is still reading it (every copy out of it was enqueued on the copy
+// stream before the loader crossed into the current epoch). Called often; does nothing most of the time.
+// Returns -1 on a CUDA error.
+int maybe_post_fill(FusedExec* ex, dm::BatchLoader* ld) {
+  const uint64_t e1 = ld->epochs + 1;
+  const int nb = static_cast<int>(e1 & 1);
+  if (ld->feed_epoch[nb] == e1) return 0;   // already posted
+  // whatever was last materialised in that buffer (normally epoch e1 - 2, long complete) must be complete: two fill
+  // jobs never write one buffer at the same time
+  if (ld->feed_epoch[nb] != dm::BatchLoader::kNoEpoch && ld->feed_rows[nb].load(std::memory_order_acquire) < ld->n) return 0;
+  const cudaError_t q = cudaStreamQuery(ex->copy);
+  if (q == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+  if (q != cudaSuccess) return fxfail("cudaStreamQuery(copy)", q);
+  auto j = std::make_shared<FillJob>();
+  j->loader = ld;
+  j->idx = ld->draw_next_perm();
+  j->x_dst = ld->feed_x[nb];
+  j->y_dst = ld->feed_y[nb];
+  j->n = static_cast<uint32_t>(ld->n);
+  j->done = &ld->feed_rows[nb];
+  ld->feed_epoch[nb] = e1;
+  ld->feed_rows[nb].store(0, std::memory_order_release);
+  ex->pool.post_fill(std::move(j));
+  ++ex->fills_posted;
+  return 0;
+}
 
 }  // namespace
 
@@ -303,6 +385,14 @@ int dm_fexec_set_lanes(void* h, int lanes) {
   return 0;
 }
 int dm_fexec_gather_threads(void* h) { return static_cast<FusedExec*>(h)->n_threads; }
+// Epoch-feed statistics: chunks fed straight from an epoch buffer, chunks that went through the gather path, epoch
+// fills posted to the helper threads.
+void dm_fexec_feed_stats(void* h, uint64_t* direct_chunks, uint64_t* gathered_chunks, uint64_t* fills_posted) {
+  FusedExec* ex = static_cast<FusedExec*>(h);
+  *direct_chunks = ex->direct_chunks;
+  *gathered_chunks = ex->gathered_chunks;
+  *fills_posted = ex->fills_posted;
+}
 
 // Debug aid (hang analysis): control words {step counter, stop word, pushes made} read through a side stream while
 // kernels may be running, plus seq / global_step of the first result slot of the chunk ring.
@@ -382,6 +472,9 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
       sz = std::min<uint32_t>(sz * 2, kChunkMax);
     }
   }
+  // epoch feed usable with this executor's ring geometry: a slot is exactly one dense batch
+  const bool feed_ok = ld->feed && ld->batch == kRowsPerSlot &&
+                       ld->x_row_bytes * kRowsPerSlot == ex->x_slot_bytes && ld->y_row_bytes * kRowsPerSlot == ex->y_slot_bytes;
   const size_t nchunks = sizes.size();
   std::vector<uint64_t> first(nchunks + 1, 0);
   for (size_t c = 0; c < nchunks; ++c) first[c + 1] = first[c] + sizes[c];
@@ -430,8 +523,35 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
       b.first_step = first[c];
       b.gathered.store(0, std::memory_order_relaxed);
       b.in_flight = true;
+      b.direct = false;
       const size_t slot0 = (c % kBuffers) * kChunkMax;
       memset(ex->res_chunks + slot0, 0, sizes[c] * sizeof(dm::StepResult));
+      if (feed_ok) {
+        const size_t rows = static_cast<size_t>(sizes[c]) * ld->batch;
+        // the current epoch's buffer is still being filled (start of a run right after a boundary, or the consumer
+        // is faster than the helpers): help finishing it — cheaper than gathering the same rows batch by batch
+        while (ld->cursor + rows <= ld->n && ld->feed_fill_in_progress()) {
+          if (!ex->pool.fill_step()) cpu_relax();
+        }
+        if (maybe_post_fill(ex, ld) != 0) { rc = -1; break; }
+        if (ld->feed_slice_ready(rows)) {
+          const int eb = static_cast<int>(ld->epochs & 1);
+          cudaError_t e = cudaMemcpyAsync(ex->x_dev + slot0 * ex->x_slot_bytes, ld->feed_x[eb] + ld->cursor * ld->x_row_bytes,
+                                          rows * ld->x_row_bytes, cudaMemcpyHostToDevice, ex->copy);
+          if (e == cudaSuccess)
+            e = cudaMemcpyAsync(ex->y_dev + slot0 * ex->y_slot_bytes, ld->feed_y[eb] + ld->cursor * ld->y_row_bytes,
+                                rows * ld->y_row_bytes, cudaMemcpyHostToDevice, ex->copy);
+          if (e == cudaSuccess) e = cudaEventRecord(b.copied, ex->copy);
+          if (e != cudaSuccess) { rc = fxfail("chunk transfer (epoch feed)", e); break; }
+          ld->skip_rows(rows);
+          b.direct = true;
+          b.gathered.store(static_cast<uint32_t>(rows), std::memory_order_release);
+          ++ex->direct_chunks;
+          ++next_gather;
+          continue;
+        }
+      }
+      ++ex->gathered_chunks;
       for (uint32_t i = 0; i < sizes[c]; ++i) {
         auto idx = std::make_shared<std::vector<uint32_t>>(ld->batch);
         ld->plan(idx->data());
@@ -460,13 +580,15 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
         else cpu_relax();
       }
       const size_t slot0 = (c % kBuffers) * kChunkMax;
-      cudaError_t e;
-      e = cudaMemcpyAsync(ex->x_dev + slot0 * ex->x_slot_bytes, ex->x_stage + slot0 * ex->x_slot_bytes,
-                          b.n * ex->x_slot_bytes, cudaMemcpyHostToDevice, ex->copy);
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(ex->y_dev + slot0 * ex->y_slot_bytes, ex->y_stage + slot0 * ex->y_slot_bytes,
-                            b.n * ex->y_slot_bytes, cudaMemcpyHostToDevice, ex->copy);
-      if (e == cudaSuccess) e = cudaEventRecord(b.copied, ex->copy);
+      cudaError_t e = cudaSuccess;
+      if (!b.direct) {   // (a chunk fed from the epoch buffer had its copies enqueued when it was planned)
+        e = cudaMemcpyAsync(ex->x_dev + slot0 * ex->x_slot_bytes, ex->x_stage + slot0 * ex->x_slot_bytes,
+                            b.n * ex->x_slot_bytes, cudaMemcpyHostToDevice, ex->copy);
+        if (e == cudaSuccess)
+          e = cudaMemcpyAsync(ex->y_dev + slot0 * ex->y_slot_bytes, ex->y_stage + slot0 * ex->y_slot_bytes,
+                              b.n * ex->y_slot_bytes, cudaMemcpyHostToDevice, ex->copy);
+        if (e == cudaSuccess) e = cudaEventRecord(b.copied, ex->copy);
+      }
       if (e == cudaSuccess) e = cudaStreamWaitEvent(ex->compute, b.copied, 0);
       if (e != cudaSuccess) { rc = fxfail("chunk transfer", e); break; }
       dm::FusedParams p = ex->params;

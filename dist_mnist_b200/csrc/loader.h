@@ -9,6 +9,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <memory>
 #include <random>
 #include <vector>
 
@@ -27,9 +29,58 @@ struct BatchLoader {
   size_t cursor = 0;
   uint64_t epochs = 0;
 
-  void reshuffle() {
-    if (shuffle) std::shuffle(perm.begin(), perm.end(), rng);
+  // ---- epoch feed (fused_exec.cu) ----
+  // TF's DataSet shuffles *physically* at an epoch boundary (`self._images = self.images[perm]`) and then hands out
+  // contiguous slices; `next_batch` between boundaries copies nothing. The epoch feed is that design with the
+  // boundary cost taken off the training thread: two pinned buffers hold the rows of the current / the next epoch in
+  // permutation order (buffer `epoch & 1`), the next epoch's buffer is filled by the executor's helper threads while
+  // the current one is being consumed, and a batch that does not straddle a boundary is a contiguous slice of pinned
+  // memory that is DMA'd to the GPU as it is. The permutation of epoch e+1 is drawn ahead of time from the same
+  // generator state the boundary would have used, so the sequence of batches is bit-identical with or without a feed.
+  static constexpr uint64_t kNoEpoch = ~0ull;
+  bool feed = false;
+  uint8_t* feed_x[2] = {nullptr, nullptr};
+  uint8_t* feed_y[2] = {nullptr, nullptr};
+  uint64_t feed_epoch[2] = {kNoEpoch, kNoEpoch};   // epoch whose rows buffer b holds / is being filled with
+  std::atomic<uint32_t> feed_rows[2];              // rows of that epoch in place
+  std::shared_ptr<std::vector<uint32_t>> next_perm;   // permutation of epoch `epochs + 1`, once drawn
+
+  BatchLoader() {
+    feed_rows[0].store(0);
+    feed_rows[1].store(0);
   }
+  BatchLoader(const BatchLoader&) = delete;
+  BatchLoader& operator=(const BatchLoader&) = delete;
+
+  // The next epoch's permutation, drawn exactly as reshuffle() would at the boundary (the generator is used by
+  // nothing else). The vector is shared with the fill job that copies the rows, so it is never modified afterwards.
+  const std::shared_ptr<std::vector<uint32_t>>& draw_next_perm() {
+    if (!next_perm) {
+      next_perm = std::make_shared<std::vector<uint32_t>>(perm);
+      if (shuffle) std::shuffle(next_perm->begin(), next_perm->end(), rng);
+    }
+    return next_perm;
+  }
+  void reshuffle() {
+    if (next_perm) {
+      perm = *next_perm;
+      next_perm.reset();
+    } else if (shuffle) {
+      std::shuffle(perm.begin(), perm.end(), rng);
+    }
+  }
+  // Rows [cursor, cursor + rows) of the current epoch are in place in its feed buffer and do not reach the boundary.
+  bool feed_slice_ready(size_t rows) const {
+    const int b = static_cast<int>(epochs & 1);
+    return feed && cursor + rows <= n && feed_epoch[b] == epochs && feed_rows[b].load(std::memory_order_acquire) >= n;
+  }
+  // The current epoch's buffer is being filled (worth waiting for instead of gathering row by row).
+  bool feed_fill_in_progress() const {
+    const int b = static_cast<int>(epochs & 1);
+    return feed && feed_epoch[b] == epochs && feed_rows[b].load(std::memory_order_acquire) < n;
+  }
+  // Consume `rows` rows of the current epoch without materialising their indices (rows <= n - cursor).
+  void skip_rows(size_t rows) { cursor += rows; }
   // next() = plan() + copy(): plan draws the batch's row indices (sequential: it owns the cursor, the epoch
   // counter and the shuffle), copy moves the rows (the expensive part; safe to run on any thread).
   void plan(uint32_t* idx_out) {

@@ -815,9 +815,19 @@ class Worker:
             return out
         return self._cpu_step(x, y)
 
-    def make_loader(self, images: torch.Tensor, labels: torch.Tensor, seed: int = 0, shuffle: bool = True):
+    def make_loader(self, images: torch.Tensor, labels: torch.Tensor, seed: int = 0, shuffle: bool = True,
+                    epoch_feed: Optional[bool] = None):
         """Native `next_batch` loader over a host dataset (kept alive by the returned object)."""
-        return NativeLoader(self, images, labels, seed, shuffle)
+        return NativeLoader(self, images, labels, seed, shuffle, epoch_feed)
+
+    def feed_stats(self) -> Dict[str, int]:
+        """Fused executor: chunks fed straight from the loader's epoch buffer / through the row gather, epoch fills
+        handed to the helper threads (all zero on other engines)."""
+        if not self._fexec:
+            return {"direct_chunks": 0, "gathered_chunks": 0, "fills_posted": 0}
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.lib.dm_fexec_feed_stats(self._fexec, C.byref(a), C.byref(b), C.byref(c))
+        return {"direct_chunks": int(a.value), "gathered_chunks": int(b.value), "fills_posted": int(c.value)}
 
     def run_steps(self, n_steps: int, loader: "NativeLoader", stop_at_global_step: int = 0,
                   wait_applied: bool = False) -> Sequence[StepOutput]:
@@ -1059,22 +1069,47 @@ class Worker:
 
 
 class NativeLoader:
-    """Host dataset + native `next_batch` gatherer (TF DataSet.next_batch semantics, csrc/executor.cu)."""
+    """Host dataset + native `next_batch` loader (TF DataSet.next_batch semantics, csrc/loader.h).
 
-    def __init__(self, worker: Worker, images: torch.Tensor, labels: torch.Tensor, seed: int = 0, shuffle: bool = True):
+    Fused engine on cuda: the loader keeps an *epoch feed* — like TF's DataSet it holds the rows of an epoch physically
+    in shuffled order (two pinned buffers: current and next epoch), so a batch is a contiguous slice of pinned memory
+    that the executor DMAs to the GPU without touching it; the next epoch's buffer is filled by the executor's helper
+    threads while the current one is consumed (csrc/fused_exec.cu). ``epoch_feed=False`` (or ``DM_EPOCH_FEED=0``)
+    keeps the row-gather path for every batch."""
+
+    def __init__(self, worker: Worker, images: torch.Tensor, labels: torch.Tensor, seed: int = 0, shuffle: bool = True,
+                 epoch_feed: Optional[bool] = None):
         self.worker = worker
         self.images = images.to(worker.tdtype).contiguous()
         self.labels = labels.to(torch.float32).contiguous()
-        if worker.cfg.backend == "cuda":
-            self.images = self.images.pin_memory()
-            self.labels = self.labels.pin_memory()
         n, pix = self.images.shape
         es = self.images.element_size()
+        ncls = self.labels.shape[1]
+        if epoch_feed is None:
+            epoch_feed = os.environ.get("DM_EPOCH_FEED", "1") != "0"
+        want_feed = (epoch_feed and worker.cfg.backend == "cuda" and worker.engine == "fused"
+                     and worker.batch == N.FUSED_ROWS_PER_SLOT and worker.ld_in == pix and n >= 1024)
+        if worker.cfg.backend == "cuda" and not want_feed:
+            self.images = self.images.pin_memory()
+            self.labels = self.labels.pin_memory()
         self.handle = worker.lib.dm_loader_create(
-            self.images.data_ptr(), self.labels.data_ptr(), n, pix * es, self.labels.shape[1] * 4,
-            worker.ld_in * es, self.labels.shape[1] * 4, worker.batch, seed, int(shuffle))
+            self.images.data_ptr(), self.labels.data_ptr(), n, pix * es, ncls * 4,
+            worker.ld_in * es, ncls * 4, worker.batch, seed, int(shuffle))
+        self._feed_bufs = None
+        if want_feed:
+            # allocated here, where the dataset used to be pinned: before an in-process ps kernel becomes resident
+            bufs = [torch.empty((n, pix), dtype=worker.tdtype, pin_memory=True) for _ in range(2)]
+            bufs += [torch.empty((n, ncls), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+            helpers = max(1, min(8, usable_cores() // 2))
+            if worker.lib.dm_loader_enable_feed(self.handle, bufs[0].data_ptr(), bufs[2].data_ptr(), bufs[1].data_ptr(),
+                                                bufs[3].data_ptr(), helpers) == 1:
+                self._feed_bufs = bufs   # kept alive with the loader
         self._xbuf = torch.zeros(worker.batch, worker.ld_in, dtype=worker.tdtype)
         self._ybuf = torch.zeros(worker.batch, self.labels.shape[1], dtype=torch.float32)
+
+    @property
+    def epoch_feed(self) -> bool:
+        return self._feed_bufs is not None
 
     def next_batch(self) -> Tuple[torch.Tensor, torch.Tensor]:
         self.worker.lib.dm_loader_next(self.handle, self._xbuf.data_ptr(), self._ybuf.data_ptr())

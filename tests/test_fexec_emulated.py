@@ -1,0 +1,67 @@
+"""The fused engine's native executor (csrc/fused_exec.cu) on an emulated CUDA runtime, on CPU.
+
+tests/native/fake_cuda/cuda_runtime.h implements the handful of runtime calls the executor uses with real threads as
+streams (asynchronous, in order, copies read their source when they *execute*), tests/native/fexec_emulated.cpp replaces
+the step kernel by a function that checksums the batch it finds in the device ring. Every step of every run must have
+seen exactly the batch the reference's `next_batch` sequence prescribes (/root/reference/distributed_server-basic.py:111)
+— through the row-gather path, the epoch-feed path, across epoch boundaries, with the loader also used from outside
+and with a StopAtStepHook-style early stop. The binary is built with AddressSanitizer + UBSan.
+"""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "dist_mnist_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.exists(os.path.join(cuda_inc, "cuda.h")):
+        pytest.skip("no cuda.h (CUtensorMap type)")
+    exe = str(tmp_path_factory.mktemp("fexec") / "fexec_emulated")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+           "-x", "c++", "-I", os.path.join(ROOT, "tests", "native", "fake_cuda"), "-I", CSRC, "-I", cuda_inc,
+           os.path.join(ROOT, "tests", "native", "fexec_emulated.cpp"), os.path.join(CSRC, "fused_exec.cu"),
+           os.path.join(CSRC, "loader_api.cpp"), "-o", exe, "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    return exe
+
+
+def run(exe, n, feed, steps, delay_us=50, threads=3):
+    env = dict(os.environ, FAKE_CUDA_DELAY_US=str(delay_us), DM_GATHER_THREADS=str(threads),
+               ASAN_OPTIONS="detect_leaks=1")
+    r = subprocess.run([exe, str(n), str(feed), str(steps)], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+    line = r.stdout.strip().splitlines()[-1]
+    assert line.startswith("OK"), line
+    return dict(kv.split("=") for kv in line.split()[1:])
+
+
+def test_gather_path_feeds_every_step_its_batch(harness):
+    s = run(harness, 3000, 0, 1200)
+    assert int(s["direct_chunks"]) == 0 and int(s["gathered_chunks"]) > 0 and int(s["epochs"]) >= 12
+
+
+def test_epoch_feed_is_bit_identical_to_next_batch(harness):
+    s = run(harness, 3000, 1, 1200)
+    # almost every chunk is a contiguous slice of the epoch buffer; only the chunks that contain a boundary gather
+    assert int(s["direct_chunks"]) > 4 * int(s["gathered_chunks"]) > 0
+    assert int(s["fills_posted"]) >= int(s["epochs"]) - 2
+
+
+def test_epoch_feed_with_slow_streams_and_fast_epochs(harness):
+    # copies and kernels take up to 300 us, an epoch is 34 steps: epoch buffers are recycled while copies are in flight
+    s = run(harness, 1100, 1, 1500, delay_us=300, threads=2)
+    assert int(s["direct_chunks"]) > 0 and int(s["epochs"]) >= 40
+
+
+def test_small_dataset_keeps_the_gather_path(harness):
+    s = run(harness, 500, 1, 400)
+    assert int(s["direct_chunks"]) == 0 and int(s["fills_posted"]) == 0
