@@ -17,21 +17,29 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "dist_mnist_b200", "csrc")
 
 
-@pytest.fixture(scope="module")
-def harness(tmp_path_factory):
+def _build(tmp_path_factory, sanitize):
     if shutil.which("g++") is None:
         pytest.skip("no g++")
     cuda_inc = "/usr/local/cuda/include"
     if not os.path.exists(os.path.join(cuda_inc, "cuda.h")):
         pytest.skip("no cuda.h (CUtensorMap type)")
     exe = str(tmp_path_factory.mktemp("fexec") / "fexec_emulated")
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
-           "-x", "c++", "-I", os.path.join(ROOT, "tests", "native", "fake_cuda"), "-I", CSRC, "-I", cuda_inc,
+    cmd = ["g++", "-O1", "-g", "-std=c++17", *sanitize, "-x", "c++", "-I", os.path.join(ROOT, "tests", "native", "fake_cuda"), "-I", CSRC, "-I", cuda_inc,
            os.path.join(ROOT, "tests", "native", "fexec_emulated.cpp"), os.path.join(CSRC, "fused_exec.cu"),
            os.path.join(CSRC, "loader_api.cpp"), "-o", exe, "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
     return exe
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    return _build(tmp_path_factory, ["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"])
+
+
+@pytest.fixture(scope="module")
+def harness_tsan(tmp_path_factory):
+    return _build(tmp_path_factory, ["-fsanitize=thread"])
 
 
 def run(exe, n, feed, steps, delay_us=50, threads=3):
@@ -65,3 +73,11 @@ def test_epoch_feed_with_slow_streams_and_fast_epochs(harness):
 def test_small_dataset_keeps_the_gather_path(harness):
     s = run(harness, 500, 1, 400)
     assert int(s["direct_chunks"]) == 0 and int(s["fills_posted"]) == 0
+
+
+def test_executor_threads_are_race_free_under_tsan(harness_tsan):
+    # training thread + gather/fill pool + two emulated streams: every hand-over (staging, epoch buffers, ring slots,
+    # result slots) must be ordered by a real synchronisation — ThreadSanitizer reports anything that is not
+    env = dict(os.environ, FAKE_CUDA_DELAY_US="100", DM_GATHER_THREADS="3", TSAN_OPTIONS="halt_on_error=1 exitcode=66")
+    r = subprocess.run([harness_tsan, "1100", "1", "700"], capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0 and "WARNING: ThreadSanitizer" not in r.stderr, (r.stdout[-1000:], r.stderr[-4000:])
