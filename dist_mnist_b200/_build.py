@@ -25,7 +25,7 @@ LIB_PATH = PKG_DIR / LIB_NAME
 CUDA_SOURCES = ["gemm_sm100.cu", "head_sm100.cu", "ps_apply_sm100.cu", "p2p_sm100.cu", "fused_step_sm100.cu",
                 "nvls_sm100.cu", "executor.cu", "fused_exec.cu", "api.cu"]
 CXX_SOURCES = ["host_runtime.cpp", "loader_api.cpp"]
-HEADERS = ["common.cuh", "protocol.h", "fused.h", "loader.h"]
+HEADERS = ["common.cuh", "protocol.h", "fused.h", "loader.h", "trace.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -120,7 +120,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
         o = BUILD_DIR / (s.stem + ".o")
         objs.append(o)
         if force or _stale(o, [s, *headers, Path(__file__)]):
-            jobs.append(["g++", *CXX_FLAGS, "-I", str(CSRC), "-c", str(s), "-o", str(o)])
+            jobs.append(["g++", *CXX_FLAGS, "-I", str(CSRC), "-I", str(cuda / "include"), "-c", str(s), "-o", str(o)])
     if jobs:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             list(ex.map(lambda c: _run(c, verbose or ptxas_info), jobs))

@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "loader.h"
+#include "trace.h"
 #include "protocol.h"
 
 namespace {
@@ -383,6 +384,7 @@ int dm_exec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uint
   Executor* ex = static_cast<Executor*>(h);
   BatchLoader* ld = static_cast<BatchLoader*>(loader);
   dm::StepResult* out = static_cast<dm::StepResult*>(out_results);
+  dm::NvtxRange nvtx_run("dm.exec.run");
   const size_t U = ex->U;
   const size_t G = ex->groups.size();
   const uint64_t first = ex->submitted + 1;
@@ -485,6 +487,7 @@ int dm_exec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uint
 int dm_exec_run_resident(void* h, uint64_t n_steps, const void* x_base, const void* y_base, size_t x_row_bytes,
                          size_t y_row_bytes, uint64_t n_rows, uint64_t batch_rows, uint64_t start) {
   Executor* ex = static_cast<Executor*>(h);
+  dm::NvtxRange nvtx_run("dm.exec.run_resident");
   const uint8_t* xb = static_cast<const uint8_t*>(x_base);
   const uint8_t* yb = static_cast<const uint8_t*>(y_base);
   const size_t U = ex->U;

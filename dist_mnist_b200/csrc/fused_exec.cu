@@ -42,6 +42,7 @@
 
 #include "fused.h"
 #include "loader.h"
+#include "trace.h"
 
 namespace {
 
@@ -286,6 +287,7 @@ int maybe_post_fill(FusedExec* ex, dm::BatchLoader* ld) {
   ld->feed_rows[nb].store(0, std::memory_order_release);
   ex->pool.post_fill(std::move(j));
   ++ex->fills_posted;
+  dm::nvtx_mark("dm.fexec.epoch_fill.posted");
   return 0;
 }
 
@@ -427,6 +429,7 @@ int dm_fexec_drain(void* h) {
 int dm_fexec_steps_host(void* h, const void* x_host, const void* y_host, uint32_t n, void* out, uint32_t* n_done) {
   FusedExec* ex = static_cast<FusedExec*>(h);
   if (!ex->have_params || n < 1 || n > kChunkMax) { g_fx_err = "steps_host: bad arguments"; return -1; }
+  dm::NvtxRange nvtx_steps("dm.fexec.steps_host");
   FX_CUDA(cudaStreamSynchronize(ex->compute));   // buffer 0 must be free
   memcpy(ex->x_stage, x_host, n * ex->x_slot_bytes);
   memcpy(ex->y_stage, y_host, n * ex->y_slot_bytes);
@@ -457,6 +460,7 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
   dm::StepResult* out = static_cast<dm::StepResult*>(out_results);
   if (!ex->have_params) { g_fx_err = "run: launch template not set"; return -1; }
   if (ld->batch != ex->batch) { g_fx_err = "run: loader batch size differs from the executor's"; return -1; }
+  dm::NvtxRange nvtx_run("dm.fexec.run");
   FX_CUDA(cudaSetDevice(ex->device));
   FX_CUDA(cudaStreamSynchronize(ex->compute));
   for (auto& b : ex->bufs) b.in_flight = false;
@@ -511,6 +515,7 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
     while (next_gather < nchunks && next_gather < next_launch + kBuffers - 1) {
       const size_t c = next_gather;
       ChunkBuf& b = ex->bufs[c % kBuffers];
+      dm::NvtxRange nvtx_plan("dm.fexec.chunk.plan");
       if (b.in_flight) {
         while (next_harvest + kBuffers <= c) {   // the previous occupant must be complete before it is overwritten
           const int hr = harvest(next_harvest, true);
@@ -574,6 +579,7 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
     {
       const size_t c = next_launch;
       ChunkBuf& b = ex->bufs[c % kBuffers];
+      dm::NvtxRange nvtx_launch("dm.fexec.chunk.launch");
       while (b.gathered.load(std::memory_order_acquire) < b.n * static_cast<uint32_t>(ld->batch)) {
         GatherTask* t = ex->pool.try_pop();
         if (t != nullptr) GatherPool::run_task(t);
@@ -651,6 +657,7 @@ int dm_fexec_run_resident(void* h, const void* maps, const void* y_base, uint64_
                           uint64_t row_wrap, uint64_t n_steps, int wait_acks, int timed) {
   FusedExec* ex = static_cast<FusedExec*>(h);
   if (!ex->have_params || n_steps == 0 || n_steps > 0xFFFFFFF0ull) { g_fx_err = "run_resident: bad arguments"; return -1; }
+  dm::NvtxRange nvtx_res("dm.fexec.run_resident");
   if (ex->last_results == ex->res_big && ex->last_n != 0) FX_CUDA(cudaEventSynchronize(ex->last_done));
   if (ex->ensure_big(n_steps) != 0) return -1;
   memset(ex->res_big, 0, n_steps * sizeof(dm::StepResult));

@@ -7,6 +7,7 @@
 #include <thread>
 
 #include "loader.h"
+#include "trace.h"
 
 using dm::BatchLoader;
 
@@ -44,6 +45,7 @@ uint64_t dm_loader_epochs(void* h) { return static_cast<BatchLoader*>(h)->epochs
 int dm_loader_enable_feed(void* h, void* x0, void* y0, void* x1, void* y1, int n_threads) {
   BatchLoader* l = static_cast<BatchLoader*>(h);
   if (l->feed) return 1;
+  dm::NvtxRange nvtx("dm.loader.enable_feed");
   if (l->x_dst_stride != l->x_row_bytes || l->y_dst_stride != l->y_row_bytes) return 0;
   if (l->n < 1024 || l->n > 0x7FFFFFFFull || l->batch < 1 || static_cast<size_t>(l->batch) * 8 > l->n) return 0;
   if (!x0 || !y0 || !x1 || !y1) return 0;

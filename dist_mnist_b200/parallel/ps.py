@@ -26,6 +26,7 @@ from ..models.mlp import MLPSpec
 from .config import EngineConfig, OptimizerConfig
 from .peer_mem import Carver, Segment
 from .sharding import ModelLayout, ShardLayout, build_layout, dw_tile_n_for
+from ..utils.metrics import nvtx_annotate
 
 CTRL_GLOBAL_STEP = 0
 CTRL_HOST_STOP = 1
@@ -161,6 +162,7 @@ class ParameterServer:
             P.inbox_table = C.addressof(self._cpu_table)
         return P
 
+    @nvtx_annotate("dm.ps.start")
     def start(self, wait_init: bool = True, timeout_s: Optional[float] = None) -> None:
         """Begin serving. Waits (like TF's non-chief `ready_op` poll) until the chief has initialised the
         variables, then launches the serve kernel / loop and announces `ps/<k>/serving`."""
@@ -198,6 +200,7 @@ class ParameterServer:
         self._serving = True
         self.rdv.put(f"ps/{self.task_index}/serving", {"mode": "oneshot" if self.oneshot else "mailbox"})
 
+    @nvtx_annotate("dm.ps.serve_once")
     def serve_once(self, after_stream: Optional[int] = None, wait: bool = True) -> None:
         """One-shot mode: launch the serve kernel once; it applies every push that is complete in memory and exits
         after the first sweep that finds nothing (csrc/ps_apply_sm100.cu, PsServeParams::oneshot). `after_stream`:
@@ -256,6 +259,7 @@ class ParameterServer:
                 new.append(w)
         return new
 
+    @nvtx_annotate("dm.ps.readmit")
     def _readmit(self, w: int) -> None:
         """Elastic recovery: worker `w` crashed and was started again. Its new life begins with push sequence 1 and
         a new inbox, so this shard drops the old incarnation's bookkeeping: the serve kernel is stopped (its
@@ -309,6 +313,7 @@ class ParameterServer:
             return host.value
         return self.lib.dm_load_acquire_u32(self.seg.addr("ctrl", 4 * CTRL_GLOBAL_STEP))
 
+    @nvtx_annotate("dm.ps.stop")
     def stop(self) -> None:
         """Ask the serve kernel / loop to exit and wait for it."""
         if not self._serving:

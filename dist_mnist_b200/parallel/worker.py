@@ -40,6 +40,7 @@ from .config import MAX_SLOTS, EngineConfig, OptimizerConfig
 from .peer_mem import Carver, Segment
 from .ps import CTRL_GLOBAL_STEP, CTRL_WORKER_DONE
 from .sharding import FUSED_CLUSTER, ModelLayout, VarLayout, build_layout, dw_tile_n_for
+from ..utils.metrics import nvtx_annotate
 
 
 @dataclass
@@ -192,6 +193,7 @@ class Worker:
         self._start_heartbeat_thread()
         self._connected = True
 
+    @nvtx_annotate("dm.worker.wait_ready")
     def wait_ready(self, timeout_s: Optional[float] = None) -> None:
         """Block until the variables are initialised (DS:108-109 non-chief wait) and every PS shard serves us."""
         self.rdv.get("init/done", timeout_s)
@@ -232,6 +234,7 @@ class Worker:
             return self._read_own("seq", 1)[0]
         return self._seq_host
 
+    @nvtx_annotate("dm.worker.wait_applied")
     def wait_applied(self, timeout_s: float = 60.0) -> None:
         """Block until every push this worker has made is applied on every shard (needed for a consistent
         checkpoint or evaluation; training itself never waits like this). GPU: a one-thread kernel on the compute
@@ -299,6 +302,7 @@ class Worker:
         self._hb_thread = threading.Thread(target=loop, name="dm-heartbeat", daemon=True)
         self._hb_thread.start()
 
+    @nvtx_annotate("dm.worker.prepare")
     def prepare(self) -> None:
         """Build the step graphs (GPU backend). Only needs the PS pointers, so it may run before the variables
         are initialised — in-process clusters call it before the persistent PS kernel is launched so that no
@@ -393,6 +397,7 @@ class Worker:
     def write_item_state(self, k: int, state: torch.Tensor) -> None:
         self._copy_to_ps(k, "item_state", 0, state.to(torch.int32))
 
+    @nvtx_annotate("dm.worker.initialize_variables")
     def initialize_variables(self, seed: int = 0, params: Optional[Dict[str, torch.Tensor]] = None) -> None:
         """Chief-only: run the initialisers on the PS shards and announce `init/done` (DS:108-109)."""
         if not self.is_chief:
@@ -829,6 +834,7 @@ class Worker:
         self.lib.dm_fexec_feed_stats(self._fexec, C.byref(a), C.byref(b), C.byref(c))
         return {"direct_chunks": int(a.value), "gathered_chunks": int(b.value), "fills_posted": int(c.value)}
 
+    @nvtx_annotate("dm.worker.run_steps")
     def run_steps(self, n_steps: int, loader: "NativeLoader", stop_at_global_step: int = 0,
                   wait_applied: bool = False) -> Sequence[StepOutput]:
         """Native train loop: n_steps x (next_batch -> H2D -> step kernels -> result D2H). `wait_applied`: return only
@@ -959,6 +965,7 @@ class Worker:
     # ------------------------------------------------------------------------------------------
     # evaluation (forward only, accuracy kernel / torch on cpu)
     # ------------------------------------------------------------------------------------------
+    @nvtx_annotate("dm.worker.evaluate")
     def evaluate(self, images: torch.Tensor, labels: torch.Tensor) -> Tuple[float, float]:
         """(mean loss, accuracy) of the current PS variables on a host dataset; GPU path uses the hand-written
         accuracy reduction kernel on torch-computed logits of the pulled variables."""

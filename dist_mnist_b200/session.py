@@ -18,7 +18,7 @@ from typing import Callable, Dict, List, Optional
 import torch
 
 from .cluster import ClusterSpec
-from .utils.metrics import TrainMetricsWriter
+from .utils.metrics import TrainMetricsWriter, nvtx_range
 from .models.mlp import MLPSpec
 from .parallel.config import EngineConfig, OptimizerConfig
 from .parallel.ps import ParameterServer
@@ -113,7 +113,8 @@ def train_loop(worker: Worker, dataset: Dataset, train_steps: int = 4000, log_ev
     stop = False
     while not stop:
         worker.heartbeat()     # liveness mark for the ps-side failure detector (--worker_timeout)
-        outs = worker.run_steps(chunk, loader, stop_at_global_step=train_steps)
+        with nvtx_range("dm.train.chunk"):
+            outs = worker.run_steps(chunk, loader, stop_at_global_step=train_steps)
         steps_run += len(outs)
         if inject_fault_after and steps_run >= inject_fault_after:
             # fault injection (tests): die like a crashed process — no finish(), no close(), no atexit handlers
@@ -132,7 +133,8 @@ def train_loop(worker: Worker, dataset: Dataset, train_steps: int = 4000, log_ev
         if chunk_sleep_s > 0:
             time.sleep(chunk_sleep_s)
         if worker.is_chief and checkpoint_dir and time.time() - last_save >= save_checkpoint_secs:
-            ckpt_path = ckpt_utils.save_checkpoint(worker, checkpoint_dir)
+            with nvtx_range("dm.train.checkpoint"):
+                ckpt_path = ckpt_utils.save_checkpoint(worker, checkpoint_dir)
             last_save = time.time()
     if worker.is_chief and checkpoint_dir:
         worker.drain()

@@ -17,6 +17,9 @@ import tempfile
 import time
 from typing import Dict, List, Optional
 
+import contextlib
+import functools
+
 import torch
 
 _QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -161,3 +164,53 @@ class TrainMetricsWriter:
         if self._fh:
             self._fh.close()
             self._fh = None
+
+
+_NVTX = None
+
+
+def _nvtx():
+    global _NVTX
+    if _NVTX is None:
+        try:
+            ok = torch.cuda.is_available()
+            from torch.cuda import nvtx as mod
+            _NVTX = mod if ok else False
+        except Exception:
+            _NVTX = False
+    return _NVTX
+
+
+@contextlib.contextmanager
+def nvtx_range(name: str):
+    """NVTX range around a host-side phase (the native runtime adds its own ranges, csrc/trace.h). A push /
+    pop is a host-only call into the NVTX shim — no CUDA synchronisation, safe next to a resident persistent kernel —
+    and a no-op on a machine without CUDA."""
+    global _NVTX
+    m = _nvtx()
+    if m:
+        try:
+            m.range_push(name)
+        except Exception:   # an unusable NVTX shim must never take training down: switch tracing off
+            _NVTX = m = False
+    if not m:
+        yield
+        return
+    try:
+        yield
+    finally:
+        try:
+            m.range_pop()
+        except Exception:
+            _NVTX = False
+
+
+def nvtx_annotate(name: str):
+    """Decorator form of nvtx_range."""
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapped(*a, **kw):
+            with nvtx_range(name):
+                return fn(*a, **kw)
+        return wrapped
+    return deco
