@@ -24,6 +24,7 @@ import collections.abc
 import ctypes as C
 import os
 import time
+import weakref
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -1102,6 +1103,9 @@ class NativeLoader:
         self.handle = worker.lib.dm_loader_create(
             self.images.data_ptr(), self.labels.data_ptr(), n, pix * es, ncls * 4,
             worker.ld_in * es, ncls * 4, worker.batch, seed, int(shuffle))
+        # destroyed when the object is collected or at interpreter exit — in both cases *before* the tensors above are
+        # released (a weakref finalizer runs ahead of the instance's own teardown)
+        self._finalizer = weakref.finalize(self, worker.lib.dm_loader_destroy, self.handle)
         self._feed_bufs = None
         if want_feed:
             # allocated here, where the dataset used to be pinned: before an in-process ps kernel becomes resident
@@ -1126,10 +1130,8 @@ class NativeLoader:
     def epochs(self) -> int:
         return int(self.worker.lib.dm_loader_epochs(self.handle))
 
-    def __del__(self):
-        try:
-            if self.handle:
-                self.worker.lib.dm_loader_destroy(self.handle)
-                self.handle = None
-        except Exception:
-            pass
+    def close(self) -> None:
+        """Destroy the native loader (waits for an epoch fill that is still running on the executor's helper threads:
+        they read the dataset and write the feed buffers this object owns)."""
+        self._finalizer()
+        self.handle = None
