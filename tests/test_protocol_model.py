@@ -1,0 +1,47 @@
+"""Exhaustive interleaving check of the fused engine's mailbox protocol (dist_mnist_b200/utils/protocol_model.py).
+
+The deferred-publish guard of csrc/fused_step_sm100.cu (`deferred = ... && (nxt - cur) < (nslots >> 1)`) exists because
+the unguarded version deadlocked on the GPU; the model reproduces that deadlock and shows that the guarded protocol, the
+immediate-publish protocol and `--strict_steps` have none, never overwrite an unconsumed mailbox slot and apply every push
+exactly once, in order — for every interleaving of every small configuration."""
+import pytest
+
+from dist_mnist_b200.parallel.config import EngineConfig, OptimizerConfig
+from dist_mnist_b200.utils.protocol_model import Config, check
+
+SMALL = [(lanes, nslots, steps) for lanes in (1, 2, 3) for nslots in range(max(2, lanes), 7) for steps in (5, 8)
+         if not (lanes == 3 and steps == 8 and nslots > 4)]
+
+
+@pytest.mark.parametrize("lanes,nslots,steps", SMALL)
+def test_guarded_deferred_publish_has_no_deadlock_and_no_slot_hazard(lanes, nslots, steps):
+    r = check(Config(lanes, nslots, steps, guard=True))
+    assert r.ok, (r.reason, r.trace)
+
+
+@pytest.mark.parametrize("lanes,nslots,steps", [(2, 4, 8), (3, 4, 8), (2, 2, 6), (3, 6, 9)])
+def test_unguarded_deferred_publish_deadlocks_like_the_first_gpu_version(lanes, nslots, steps):
+    r = check(Config(lanes, nslots, steps, guard=False))
+    assert not r.ok and r.reason.startswith("deadlock"), r.reason
+    # the cycle: some lane's flow control waits for an acknowledgement the ps cannot give because the push it needs
+    # next is still unpublished
+    assert "ps waits for push" in r.reason and r.trace
+
+
+@pytest.mark.parametrize("lanes,nslots,steps", [(1, 2, 6), (2, 2, 7), (2, 4, 8), (3, 3, 7), (3, 6, 8)])
+def test_strict_and_immediate_publish_variants(lanes, nslots, steps):
+    assert check(Config(lanes, nslots, steps, strict=True)).ok
+    assert check(Config(lanes, nslots, steps, defer=False)).ok
+
+
+def test_single_lane_needs_no_guard():
+    # one lane claims consecutive steps: (nxt - cur) == 1 < nslots, its deferred push is never what its own flow control
+    # waits for as long as the ring has at least 2 slots
+    assert check(Config(1, 2, 8, guard=False)).ok
+    assert check(Config(1, 4, 8, guard=False)).ok
+
+
+def test_engine_config_keeps_the_ring_at_least_as_deep_as_the_lanes():
+    # the model's precondition nslots >= lanes is what EngineConfig.validate enforces for the real engine
+    with pytest.raises(ValueError):
+        EngineConfig(backend="cpu", lanes=4, nslots=2).validate(OptimizerConfig("adam", 1e-4))
