@@ -485,8 +485,16 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
   const bool trace = getenv("DM_FEXEC_TRACE") != nullptr;
   const auto t_begin = std::chrono::steady_clock::now();
   auto us_since = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(); };
-  ex->pool.active.fetch_add(1, std::memory_order_release);
-  ex->pool.cv.notify_all();
+  // The helper threads are woken (and kept spinning for the rest of the run) only when a chunk actually needs rows
+  // gathered: a run fed entirely from the epoch buffer never touches them — waking a dozen parked threads costs the
+  // training thread tens of microseconds, a sizeable part of a 20-step call.
+  bool pool_active = false;
+  auto activate_pool = [&] {
+    if (pool_active) return;
+    pool_active = true;
+    ex->pool.active.fetch_add(1, std::memory_order_release);
+    ex->pool.cv.notify_all();
+  };
   uint64_t total_done = 0;
   bool stop = false;
   size_t next_gather = 0, next_launch = 0, next_harvest = 0;
@@ -557,6 +565,7 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
         }
       }
       ++ex->gathered_chunks;
+      activate_pool();
       for (uint32_t i = 0; i < sizes[c]; ++i) {
         auto idx = std::make_shared<std::vector<uint32_t>>(ld->batch);
         ld->plan(idx->data());
@@ -636,7 +645,7 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
     }
     b.in_flight = false;
   }
-  ex->pool.active.fetch_sub(1, std::memory_order_release);
+  if (pool_active) ex->pool.active.fetch_sub(1, std::memory_order_release);
   if (rc != 0) return rc;
   FX_CUDA(cudaStreamSynchronize(ex->compute));
   if (trace) fprintf(stderr, "[fexec] run of %llu steps drained at +%.1f us (%d gather threads)\n",
