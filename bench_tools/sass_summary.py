@@ -9,13 +9,15 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 KEEP = re.compile(r"^(UTC|LDTM|STTM|UTMA|UBLKCP|SYNCS|RED|ATOM|MEMBAR|CCTL|UCGABAR|ACQBULK|PREEXIT|MUFU\.(RCP|SQRT|RSQ|EX2|LG2)|"
-                  r"ERRBAR|FENCE|LDG\.E\.STRONG|STG\.E\.STRONG|LD\.E\.STRONG|ST\.E\.STRONG|STS\..*CLUSTER|ST\.E.*CLUSTER|MAPA|"
+                  r"ERRBAR|FENCE|LDGMC|LDG\.E\.(\d+\.)?STRONG|STG\.E\.(\d+\.)?STRONG|LD\.E\.STRONG|ST\.E\.STRONG|STS\..*CLUSTER|ST\.E.*CLUSTER|MAPA|"
                   r"UMOV.*SR_CgaCtaId|S2UR)")
 HEADER = """SASS mnemonic evidence per kernel of libdmnist_sm100a.so (cuobjdump -sass, sm_100a); regenerate with
 `python -m bench_tools.sass_summary`.
 UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, UTMALDG = cp.async.bulk.tensor (TMA), UBLKCP = cp.async.bulk,
 SYNCS = mbarrier, UCGABAR = barrier.cluster, ACQBULK / PREEXIT = griddepcontrol.wait / launch_dependents (PDL),
-RED/REDG = red.global (atomic push, monotone acks), *.STRONG.SYS = system-scope flag ld/st, MUFU.RCP/SQRT = Adam fast path
+RED/REDG = red.global (atomic push, monotone acks), *.STRONG.SYS = system-scope flag ld/st, MUFU.RCP/SQRT = Adam fast path,
+LDGMC.E.ADD.F32x4 = multimem.ld_reduce (in-switch sum over an NVLS multicast team); multimem.st is an STG.E.128.STRONG.SYS whose
+address is a multicast mapping (nvls_sm100.cu)
 """
 
 
