@@ -257,8 +257,9 @@ def check_accuracy() -> bool:
     return ok
 
 
-def check_ps_serve() -> bool:
-    """Single-GPU test of the persistent PS kernel: mailboxes and inboxes are local buffers."""
+def check_ps_serve(ieee: bool = False) -> bool:
+    """Single-GPU test of the persistent PS kernel: mailboxes and inboxes are local buffers. `ieee`: the
+    `--adam_math ieee` instantiation (correctly rounded sqrt / divide)."""
     from dist_mnist_b200 import _native as N
     ok = True
     dev = "cuda"
@@ -315,6 +316,7 @@ def check_ps_serve() -> bool:
         P.n_items, P.n_workers, P.nslots, P.opt, P.apply_mode = n_items, n_workers, nslots, opt, apply_mode
         P.n_flags = n_items
         P.lr, P.beta1, P.beta2, P.eps = 1e-2, 0.9, 0.999, 1e-8
+        P.ieee_math = 1 if ieee else 0
         P.mailbox, P.arena_elems = mailbox.data_ptr(), arena
         P.flags, P.next_seq, P.consumed = flags.data_ptr(), next_seq.data_ptr(), consumed.data_ptr()
         P.global_step, P.worker_done, P.host_stop = gstep.data_ptr(), done.data_ptr(), stop.data_ptr()
@@ -349,7 +351,7 @@ def check_ps_serve() -> bool:
         gs = int(gstep.item())
         acks = inbox[:, 0].tolist()
         good = e < 1e-5 and gs == n_workers * n_push and acks == [n_push] * n_workers and e_sh < 1e-3
-        ok &= report(f"ps_serve opt={opt} mode={apply_mode}", good,
+        ok &= report(f"ps_serve opt={opt} mode={apply_mode} math={'ieee' if ieee else 'fast'}", good,
                      f"param_err={e:.1e} shadow_err={e_sh:.1e} global_step={gs} acks={acks} exit={int(exitc.item())}")
     return ok
 

@@ -108,7 +108,7 @@ class PsServeParams(C.Structure):
         ("inbox_table", C.c_void_p),
         ("exit_counter", C.c_void_p),
         ("gpu_scope", C.c_uint32), ("lookahead", C.c_uint32),
-        ("oneshot", C.c_uint32), ("pad2_", C.c_uint32),
+        ("oneshot", C.c_uint32), ("ieee_math", C.c_uint32),
         ("stats", C.c_void_p),
     ]
 

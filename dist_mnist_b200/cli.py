@@ -66,6 +66,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--task_index", type=int, default=None)
     # ---- new-engine flags ----
     p.add_argument("--optimizer", choices=["adam", "sgd"], default="adam", help="reference uses Adam (DS:102)")
+    p.add_argument("--adam_math", choices=["fast", "ieee"], default="fast",
+                   help="ps-side Adam arithmetic (cuda): MUFU sqrt/reciprocal (default) or correctly rounded like TF's ApplyAdam")
     p.add_argument("--model", choices=["book", "zhihu", "wide"], default="book")
     p.add_argument("--dtype", choices=["fp32", "bf16"], default="fp32")
     p.add_argument("--backend", choices=["auto", "cuda", "cpu"], default="auto")
@@ -140,7 +142,7 @@ def run(args: argparse.Namespace) -> int:
     cluster.task_endpoint(args.job_name, args.task_index)
     backend = resolve_backend(args.backend)
     spec = mlp.get_model(args.model, args.hidden_units)
-    opt = OptimizerConfig(args.optimizer, args.learning_rate)
+    opt = OptimizerConfig(args.optimizer, args.learning_rate, math=args.adam_math)
     cfg = engine_config_from_args(args, backend)
     cfg.validate(opt)
     device = -1

@@ -181,7 +181,8 @@ struct PsServeParams {
   uint32_t gpu_scope;          // 1: every worker runs on the PS's own GPU (flags / acks at gpu scope)
   uint32_t lookahead;          // max pushes of one worker consumed per item pass (0 = auto: up to nslots)
   uint32_t oneshot;            // 1: apply whatever is pending and exit after the first full sweep that finds nothing
-  uint32_t pad2_;              //    (stream-ordered after the workers' kernels: profiler / sanitizer safe)
+  uint32_t ieee_math;          //    (stream-ordered after the workers' kernels: profiler / sanitizer safe)
+                               // ieee_math 1: Adam with correctly rounded sqrt / divide (`--adam_math ieee`)
   // Optional per-CTA serve statistics [gridDim.x][8] (accumulated over launches, written when a CTA exits):
   // passes with work, pushes applied, cycles in apply, cycles in bookkeeping, idle poll rounds, cycles idle,
   // largest number of pushes taken in one pass, poll cycles of working passes. Null = off.

@@ -24,6 +24,13 @@ class OptimizerConfig:
     beta1: float = 0.9
     beta2: float = 0.999
     eps: float = 1e-8
+    math: str = "fast"          # ps-side Adam arithmetic on the cuda backend: "fast" (MUFU sqrt / reciprocal, <= 2 ulp,
+                                # the measured configuration) | "ieee" (correctly rounded sqrt and divide, like TF's
+                                # ApplyAdam; ~4x the per-push apply cost). The cpu backend is always IEEE.
+
+    def __post_init__(self):
+        if self.math not in ("fast", "ieee"):
+            raise ValueError(f"unknown adam math {self.math!r} (fast | ieee)")
 
     @property
     def native_kind(self) -> int:

@@ -145,6 +145,7 @@ class ParameterServer:
         P.oneshot = 0
         P.opt, P.apply_mode = opt.native_kind, cfg.native_apply_mode
         P.lr, P.beta1, P.beta2, P.eps = opt.lr, opt.beta1, opt.beta2, opt.eps
+        P.ieee_math = 1 if opt.math == "ieee" else 0
         P.mailbox, P.arena_elems = s.addr("mailbox"), sh.arena_elems
         P.flags, P.next_seq, P.consumed = s.addr("flags"), s.addr("next_seq"), s.addr("consumed")
         P.global_step = s.addr("ctrl", 4 * CTRL_GLOBAL_STEP)

@@ -64,3 +64,23 @@ def test_engine_flags_defaults_are_the_benchmarked_engine_and_lanes_1_is_the_ref
     a = cli.build_parser().parse_args(["--lanes", "4", "--graph_steps=2", "--nslots", "4"])
     cfg = cli.engine_config_from_args(a, "cpu")
     assert (cfg.nslots, cfg.lanes, cfg.graph_steps) == (4, 4, 2)
+
+
+def test_adam_math_flag_selects_the_ieee_ps_kernel():
+    import pytest
+    from dist_mnist_b200 import _native as N
+    from dist_mnist_b200.parallel.config import OptimizerConfig
+
+    a = cli.build_parser().parse_args([])
+    assert a.adam_math == "fast"                       # the measured configuration (MUFU sqrt / reciprocal)
+    a = cli.build_parser().parse_args(["--adam_math", "ieee"])
+    assert OptimizerConfig(a.optimizer, a.learning_rate, math=a.adam_math).math == "ieee"
+    with pytest.raises(ValueError):
+        OptimizerConfig("adam", 1e-4, math="exact")
+    assert "ieee_math" in [f[0] for f in N.PsServeParams._fields_]
+    # both instantiations of the serve kernel are in the library
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump"):
+        syms = subprocess.run(["cuobjdump", "-elf", str(N.lib_path())], capture_output=True, text=True).stdout
+        assert "ps_serve_kernelILb0EE" in syms and "ps_serve_kernelILb1EE" in syms

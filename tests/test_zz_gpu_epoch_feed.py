@@ -47,3 +47,11 @@ def test_epoch_feed_steps_see_the_next_batch_sequence():
     # 36 chunks in all; the 6 that contain an epoch boundary are row-gathered, the rest are slices of an epoch buffer
     # (unless a fill could not be posted in time, which only costs speed)
     assert stats["direct_chunks"] > 0 and stats["gathered_chunks"] >= 6 and stats["fills_posted"] >= 3
+
+
+def test_ps_serve_kernel_ieee_adam_math():
+    """`--adam_math ieee` (PsServeParams::ieee_math): the second instantiation of ps_serve_kernel, with correctly
+    rounded sqrt / divide like TF's ApplyAdam, against the same PyTorch fp32 reference as the default fast path
+    (tests/test_gpu_kernels.py::test_persistent_ps_serve_kernel)."""
+    from bench_tools import gpu_check
+    assert gpu_check.check_ps_serve(ieee=True)
