@@ -53,9 +53,10 @@ class EngineConfig:
     engine: str = "auto"             # "fused": one persistent kernel runs whole steps (784-H-10 models, H <= 128,
                                      # batch <= 32, fp32) | "graph": per-layer kernels chained in a CUDA graph (any
                                      # model / dtype) | "auto": fused when the model is eligible
-    strict_steps: bool = False       # fused engine: a lane pulls the weights of its next step only after the ps has
-                                     # acknowledged its previous push (the reference's read-your-writes order inside
-                                     # one worker); default: the pull overlaps the previous step's backward half
+    strict_steps: bool = False       # fused engine and cpu backend: a lane pulls the weights of its next step only
+                                     # after the ps has acknowledged its previous push (the reference's read-your-writes
+                                     # order inside one worker); default: the pull overlaps the previous step's backward
+                                     # half. (The per-layer graph engine has no strict mode: use step() + wait_applied().)
     ps_row_blocks: int = 4           # fused tiling: ps items (CTAs) per pushed column slice of the hidden weight
     ps_mode: str = "persistent"      # "persistent": resident serve kernel | "oneshot": the serve kernel is launched
                                      # after the workers' kernels, applies what is pending and exits (in-process

@@ -956,6 +956,12 @@ class Worker:
             v = views[k]
             for flag in range(lay.shards[k].n_flags):
                 self.lib.dm_store_release_u32(v["flags_addr"] + 4 * (slot * v["ni"] + flag), seq)
+        if self.inbox_order and self.cfg.strict_steps:
+            # --strict_steps (reference order inside one worker, DS:110-113): the step returns — and the next pull
+            # happens — only after every shard has applied this push
+            for k, i in self.inbox_index.items():
+                if self.lib.dm_wait_ge_u32(self._inbox_addr + 8 * i, seq, 120.0) != 0:
+                    raise TimeoutError(f"ps {k} did not acknowledge push {seq}")
         if self.inbox_order:
             ack = self.lib.dm_load_acquire_u32(self._inbox_addr)
             gstep = self.lib.dm_load_acquire_u32(self._inbox_addr + 4) + (seq - ack)

@@ -1,0 +1,42 @@
+"""`--strict_steps` on the CPU plumbing backend: with one worker and one step in flight every pull follows the
+acknowledgement of the previous push (the reference's `sess.run` order, /root/reference/distributed_server-basic.py:
+110-113), so the native train loop is comparable step by step with a plain PyTorch re-implementation fed by the same
+`next_batch` sequence. This is also the CPU twin of tests/test_zz_gpu_epoch_feed.py (same reference logic)."""
+import pytest
+import torch
+
+from dist_mnist_b200.models import mlp
+from dist_mnist_b200.parallel.config import EngineConfig, OptimizerConfig
+from dist_mnist_b200.session import InProcessCluster
+from dist_mnist_b200.utils import data
+
+
+@pytest.mark.parametrize("okind,lr,tol", [("sgd", 0.05, 1e-6), ("adam", 1e-3, 2e-4)])
+def test_strict_native_loop_is_lock_step_with_the_fp32_reference(okind, lr, tol):
+    from bench_tools.gpu_e2e import ref_step
+
+    ds = data.synthetic_mnist(1024, seed=9)            # 32 steps per epoch
+    spec = mlp.book_model(100)
+    params = mlp.init_params(spec, seed=3)
+    opt = OptimizerConfig(okind, lr)
+    cfg = EngineConfig(backend="cpu", lanes=1, nslots=4, strict_steps=True)
+    ref_p = {k: t.clone() for k, t in params.items()}
+    ref_m = {k: torch.zeros_like(t) for k, t in params.items()}
+    ref_v = {k: torch.zeros_like(t) for k, t in params.items()}
+    with InProcessCluster(spec, opt, cfg, batch_size=32, num_ps=1, params=params) as cl:
+        w = cl.worker
+        loader = w.make_loader(ds.images, ds.labels, seed=7)
+        twin = w.make_loader(ds.images, ds.labels, seed=7, epoch_feed=False)   # same sequence
+        outs = []
+        for n in (5, 20, 50, 45):                      # 120 steps = 3.75 epochs
+            outs += list(w.run_steps(n, loader))
+        t = 0
+        for o in outs:
+            x, y = twin.next_batch()
+            lref, t = ref_step(spec, ref_p, ref_m, ref_v, t, x, y, opt)
+            assert abs(o.loss - lref) <= tol * abs(lref) + 1e-9, (o.seq, o.loss, lref)
+            assert o.global_step == o.seq              # every earlier push had been applied when the step ran
+        assert loader.epochs == twin.epochs == 3
+        got = w.read_variables()
+    for k in got:
+        assert float((got[k] - ref_p[k]).norm() / (ref_p[k].norm() + 1e-12)) < 1e-3, k
