@@ -114,11 +114,13 @@ int main(int argc, char** argv) {
 
   std::vector<float> bx(B * I), by(B * C);
   uint64_t done_total = 0, seq_expected = 0;
-  std::mt19937 rng(7);
+  const unsigned seed = argc > 4 ? static_cast<unsigned>(atoi(argv[4])) : 0u;   // != 0: random run lengths
+  std::mt19937 rng(seed ? seed : 7u);
   const uint64_t run_sizes[] = {5, 20, 1, 50, 16, 37, 100, 4, 333};
   size_t k = 0;
   while (done_total < total) {
-    const uint64_t want = run_sizes[k++ % (sizeof(run_sizes) / sizeof(run_sizes[0]))];
+    const uint64_t want = seed != 0 ? 1 + rng() % 120 : run_sizes[k % (sizeof(run_sizes) / sizeof(run_sizes[0]))];
+    ++k;
     if (k % 5 == 0) {   // the loader is also used from outside the executor (Python's next_batch): must stay coherent
       dm_loader_next(ld, bx.data(), by.data());
       std::vector<float> rx(B * I), ry(B * C);

@@ -42,10 +42,11 @@ def harness_tsan(tmp_path_factory):
     return _build(tmp_path_factory, ["-fsanitize=thread"])
 
 
-def run(exe, n, feed, steps, delay_us=50, threads=3):
+def run(exe, n, feed, steps, delay_us=50, threads=3, seed=0):
     env = dict(os.environ, FAKE_CUDA_DELAY_US=str(delay_us), DM_GATHER_THREADS=str(threads),
                ASAN_OPTIONS="detect_leaks=1")
-    r = subprocess.run([exe, str(n), str(feed), str(steps)], capture_output=True, text=True, env=env, timeout=600)
+    r = subprocess.run([exe, str(n), str(feed), str(steps), str(seed)], capture_output=True, text=True, env=env,
+                       timeout=600)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
     line = r.stdout.strip().splitlines()[-1]
     assert line.startswith("OK"), line
@@ -81,3 +82,14 @@ def test_executor_threads_are_race_free_under_tsan(harness_tsan):
     env = dict(os.environ, FAKE_CUDA_DELAY_US="100", DM_GATHER_THREADS="3", TSAN_OPTIONS="halt_on_error=1 exitcode=66")
     r = subprocess.run([harness_tsan, "1100", "1", "700"], capture_output=True, text=True, env=env, timeout=900)
     assert r.returncode == 0 and "WARNING: ThreadSanitizer" not in r.stderr, (r.stdout[-1000:], r.stderr[-4000:])
+
+
+def test_random_geometries(harness):
+    # seeded sweep over dataset size (epoch length), run lengths, stream latency and helper-thread count
+    import random
+    rnd = random.Random(20260921)
+    for _ in range(12):
+        n = rnd.choice([1024, 1056, 1500, 2048, 3333, 4096 + 17])
+        s = run(harness, n, 1, rnd.randint(300, 900), delay_us=rnd.choice([0, 20, 150]), threads=rnd.choice([1, 2, 4]),
+                seed=rnd.randint(1, 10 ** 6))
+        assert int(s["direct_chunks"]) > 0
