@@ -16,11 +16,15 @@
 #include <functional>
 #include <mutex>
 #include <random>
+#include <set>
 #include <thread>
+#include <vector>
 
 typedef int cudaError_t;
 enum : int { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorNotReady = 600 };
-enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3,
+                      cudaMemcpyDefault = 4 };
+enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal = 0, cudaStreamCaptureModeThreadLocal = 1, cudaStreamCaptureModeRelaxed = 2 };
 enum : unsigned { cudaHostAllocDefault = 0, cudaHostAllocPortable = 1, cudaHostAllocMapped = 2 };
 enum : unsigned { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
 
@@ -44,7 +48,29 @@ struct Event {
   std::condition_variable cv;
   uint64_t recorded = 0, completed = 0;
   std::chrono::steady_clock::time_point when;
+  uint64_t captured_in = 0;   // id of the stream capture this event was last recorded in (0: recorded for real)
 };
+
+// Stream capture: operations issued to a capturing stream (the origin and every stream that joined through an event
+// wait) are appended to the graph in call order instead of being executed. Call order is one valid topological order
+// of the captured dependency graph, so a launch replays the operations sequentially on the launching stream.
+struct Graph {
+  std::vector<std::function<void()>> ops;
+};
+struct Stream;
+struct Capture {
+  uint64_t id = 0;
+  Graph* graph = nullptr;
+  std::set<Stream*> members;
+};
+inline Capture*& current_capture() {
+  static Capture* c = nullptr;
+  return c;
+}
+inline uint64_t& capture_counter() {
+  static uint64_t n = 0;
+  return n;
+}
 
 struct Stream {
   std::mutex mu;
@@ -59,7 +85,9 @@ struct Stream {
     cv.notify_all();
     th.join();
   }
+  bool capturing() { Capture* c = current_capture(); return c != nullptr && c->members.count(this) != 0; }
   void push(std::function<void()> f) {
+    if (capturing()) { current_capture()->graph->ops.push_back(std::move(f)); return; }
     { std::lock_guard<std::mutex> lk(mu); q.push_back(std::move(f)); ++enq; }
     cv.notify_all();
   }
@@ -93,6 +121,8 @@ struct Stream {
 
 typedef fakecuda::Stream* cudaStream_t;
 typedef fakecuda::Event* cudaEvent_t;
+typedef fakecuda::Graph* cudaGraph_t;
+typedef fakecuda::Graph* cudaGraphExec_t;
 
 inline const char* cudaGetErrorName(cudaError_t e) { return e == cudaSuccess ? "cudaSuccess" : e == cudaErrorNotReady ? "cudaErrorNotReady" : "cudaErrorFake"; }
 inline const char* cudaGetErrorString(cudaError_t e) { return cudaGetErrorName(e); }
@@ -111,6 +141,8 @@ inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { return cudaEventCreateWithFlags(e, 0); }
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) {
+  if (s->capturing()) { e->captured_in = fakecuda::current_capture()->id; return cudaSuccess; }
+  e->captured_in = 0;
   uint64_t ticket;
   { std::lock_guard<std::mutex> lk(e->mu); ticket = ++e->recorded; }
   s->push([e, ticket] {
@@ -134,6 +166,9 @@ inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
   return cudaSuccess;
 }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned) {
+  if (fakecuda::Capture* c = fakecuda::current_capture()) {
+    if (e->captured_in == c->id) { c->members.insert(s); return cudaSuccess; }   // fork / join inside the capture
+  }
   uint64_t ticket;
   { std::lock_guard<std::mutex> lk(e->mu); ticket = e->recorded; }   // the most recent record at the time of the call
   s->push([e, ticket] {
@@ -149,3 +184,42 @@ inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMem
   });
   return cudaSuccess;
 }
+inline cudaError_t cudaMemcpy(void* dst, const void* src, size_t n, cudaMemcpyKind) { memcpy(dst, src, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                                     cudaMemcpyKind, cudaStream_t s) {
+  s->push([=] {
+    fakecuda::random_delay();
+    for (size_t r = 0; r < height; ++r)
+      memcpy(static_cast<char*>(dst) + r * dpitch, static_cast<const char*>(src) + r * spitch, width);
+  });
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t s, cudaStreamCaptureMode) {
+  if (fakecuda::current_capture() != nullptr) return cudaErrorInvalidValue;
+  fakecuda::Capture* c = new fakecuda::Capture();
+  c->id = ++fakecuda::capture_counter();
+  c->graph = new fakecuda::Graph();
+  c->members.insert(s);
+  fakecuda::current_capture() = c;
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamEndCapture(cudaStream_t s, cudaGraph_t* g) {
+  fakecuda::Capture* c = fakecuda::current_capture();
+  if (c == nullptr || c->members.count(s) == 0) return cudaErrorInvalidValue;
+  *g = c->graph;
+  fakecuda::current_capture() = nullptr;
+  delete c;
+  return cudaSuccess;
+}
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t g, unsigned long long) {
+  *e = new fakecuda::Graph(*g);
+  return cudaSuccess;
+}
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t s) {
+  s->push([e] {
+    for (auto& op : e->ops) op();
+  });
+  return cudaSuccess;
+}
+inline cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e) { delete e; return cudaSuccess; }
