@@ -1115,11 +1115,16 @@ class NativeLoader:
         self._feed_bufs = None
         if want_feed:
             # allocated here, where the dataset used to be pinned: before an in-process ps kernel becomes resident
-            bufs = [torch.empty((n, pix), dtype=worker.tdtype, pin_memory=True) for _ in range(2)]
-            bufs += [torch.empty((n, ncls), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+            try:
+                bufs = [torch.empty((n, pix), dtype=worker.tdtype, pin_memory=True) for _ in range(2)]
+                bufs += [torch.empty((n, ncls), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+            except RuntimeError as e:   # no room for two pinned copies of the dataset: keep the row-gather path
+                print(f"[worker {worker.task_index}] epoch feed disabled (pinned allocation failed: {e})", flush=True)
+                bufs = None
             helpers = max(1, min(8, usable_cores() // 2))
-            if worker.lib.dm_loader_enable_feed(self.handle, bufs[0].data_ptr(), bufs[2].data_ptr(), bufs[1].data_ptr(),
-                                                bufs[3].data_ptr(), helpers) == 1:
+            if bufs is not None and worker.lib.dm_loader_enable_feed(
+                    self.handle, bufs[0].data_ptr(), bufs[2].data_ptr(), bufs[1].data_ptr(), bufs[3].data_ptr(),
+                    helpers) == 1:
                 self._feed_bufs = bufs   # kept alive with the loader
         self._xbuf = torch.zeros(worker.batch, worker.ld_in, dtype=worker.tdtype)
         self._ybuf = torch.zeros(worker.batch, self.labels.shape[1], dtype=torch.float32)
