@@ -51,4 +51,6 @@ def test_every_step_sees_its_batch(harness, nslots, lanes, graph_steps):
 def test_gather_ring_and_slot_reuse_are_race_free_under_tsan(harness_tsan):
     env = dict(os.environ, FAKE_CUDA_DELAY_US="100", DM_GATHER_THREADS="3", TSAN_OPTIONS="halt_on_error=1 exitcode=66")
     r = subprocess.run([harness_tsan, "8", "4", "2", "400"], capture_output=True, text=True, env=env, timeout=900)
+    if "unexpected memory mapping" in r.stderr:      # TSan runtime vs. this kernel's ASLR settings: not our bug
+        pytest.skip("ThreadSanitizer cannot run on this kernel (unexpected memory mapping)")
     assert r.returncode == 0 and "WARNING: ThreadSanitizer" not in r.stderr, (r.stdout[-1000:], r.stderr[-4000:])

@@ -81,6 +81,8 @@ def test_executor_threads_are_race_free_under_tsan(harness_tsan):
     # result slots) must be ordered by a real synchronisation — ThreadSanitizer reports anything that is not
     env = dict(os.environ, FAKE_CUDA_DELAY_US="100", DM_GATHER_THREADS="3", TSAN_OPTIONS="halt_on_error=1 exitcode=66")
     r = subprocess.run([harness_tsan, "1100", "1", "700"], capture_output=True, text=True, env=env, timeout=900)
+    if "unexpected memory mapping" in r.stderr:      # TSan runtime vs. this kernel's ASLR settings: not our bug
+        pytest.skip("ThreadSanitizer cannot run on this kernel (unexpected memory mapping)")
     assert r.returncode == 0 and "WARNING: ThreadSanitizer" not in r.stderr, (r.stdout[-1000:], r.stderr[-4000:])
 
 
