@@ -94,3 +94,20 @@ def test_documented_topology_one_process_per_gpu(n_ps, extra):
     total = sum(_local_steps(o) for o in outs_w)
     owner = [int(m.group(1)) for o in outs_p for m in [re.search(r"global_step=(\d+) owns_global_step=1", o)] if m]
     assert owner and owner[0] == total >= 2000, (owner, total, outs_p)
+
+
+def test_nvls_multicast_publish_and_in_switch_reduce():
+    """NVSwitch multicast over every visible GPU of this process (csrc/nvls_sm100.cu): `multimem.st` publish lands bit
+    for bit in every replica, `multimem.ld_reduce` returns the exact sum over the replicas. Run in a fresh process
+    (the probe creates VMM mappings and enables peer access itself). Measured: profiles/r2/nvls_probe.md."""
+    _need_gpus(2)
+    n = min(torch.cuda.device_count(), 8)
+    code = ("from dist_mnist_b200 import _native as N\n"
+            f"ok, log = N.nvls_probe({n}, 318032, 20)\n"
+            "print(log)\n"
+            "raise SystemExit(0 if ok else 1)\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT,
+                       env=dict(os.environ, PYTHONPATH=ROOT), timeout=300)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0 and "PROBE OK" in r.stdout, (r.stdout[-3000:], r.stderr[-2000:])
+    assert "0 of 79508 floats differ" in r.stdout
