@@ -561,7 +561,10 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
           b.gathered.store(static_cast<uint32_t>(rows), std::memory_order_release);
           ++ex->direct_chunks;
           ++next_gather;
-          continue;
+          // nothing to wait for: launch what is planned before planning further ahead (the copies of the following
+          // chunk are enqueued right after this chunk's launch and still overlap its kernel); planning three chunks
+          // ahead first would only delay the first launch of a short run by the host time of six copy calls
+          break;
         }
       }
       ++ex->gathered_chunks;
