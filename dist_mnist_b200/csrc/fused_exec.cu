@@ -224,6 +224,8 @@ struct FusedExec {
   uint64_t direct_chunks = 0, gathered_chunks = 0, fills_posted = 0;   // feed statistics (dm_fexec_feed_stats)
   ChunkBuf bufs[kBuffers];
   GatherPool pool;
+  cudaEvent_t feed_read[2] = {nullptr, nullptr};     // epoch feed: last H2D copy that reads epoch buffer b (copy stream)
+  bool feed_read_valid[2] = {false, false};
   cudaEvent_t t_start = nullptr, t_stop = nullptr;   // timing events of a timed resident launch
   cudaEvent_t last_done = nullptr;  // completion of the most recent launch
   uint64_t last_n = 0;              // steps requested by the most recent resident launch
@@ -273,9 +275,15 @@ int maybe_post_fill(FusedExec* ex, dm::BatchLoader* ld) {
   // whatever was last materialised in that buffer (normally epoch e1 - 2, long complete) must be complete: two fill
   // jobs never write one buffer at the same time
   if (ld->feed_epoch[nb] != dm::BatchLoader::kNoEpoch && ld->feed_rows[nb].load(std::memory_order_acquire) < ld->n) return 0;
-  const cudaError_t q = cudaStreamQuery(ex->copy);
-  if (q == cudaErrorNotReady) { cudaGetLastError(); return 0; }
-  if (q != cudaSuccess) return fxfail("cudaStreamQuery(copy)", q);
+  // ... and no H2D copy may still be reading it: every copy out of that buffer was enqueued before the loader crossed
+  // into the current epoch, the last of them followed by feed_read[nb]. (Asking whether the whole copy stream is idle
+  // would almost never succeed in a pipelined run: the current epoch's copies keep it busy.)
+  if (ex->feed_read_valid[nb]) {
+    const cudaError_t q = cudaEventQuery(ex->feed_read[nb]);
+    if (q == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+    if (q != cudaSuccess) return fxfail("cudaEventQuery(feed_read)", q);
+    ex->feed_read_valid[nb] = false;
+  }
   auto j = std::make_shared<FillJob>();
   j->loader = ld;
   j->idx = ld->draw_next_perm();
@@ -334,6 +342,7 @@ int dm_fexec_create(int device, int lanes, int I, int C, int batch, void** out) 
     FX_CUDA(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
   }
   FX_CUDA(cudaEventCreateWithFlags(&ex->last_done, cudaEventDisableTiming));
+  for (auto& e : ex->feed_read) FX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   FX_CUDA(cudaEventCreate(&ex->t_start));
   FX_CUDA(cudaEventCreate(&ex->t_stop));
   if (ex->ensure_big(1u << 16) != 0) return -1;   // up front: no pinned allocation while a persistent ps kernel is resident
@@ -555,7 +564,9 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
             e = cudaMemcpyAsync(ex->y_dev + slot0 * ex->y_slot_bytes, ld->feed_y[eb] + ld->cursor * ld->y_row_bytes,
                                 rows * ld->y_row_bytes, cudaMemcpyHostToDevice, ex->copy);
           if (e == cudaSuccess) e = cudaEventRecord(b.copied, ex->copy);
+          if (e == cudaSuccess) e = cudaEventRecord(ex->feed_read[eb], ex->copy);
           if (e != cudaSuccess) { rc = fxfail("chunk transfer (epoch feed)", e); break; }
+          ex->feed_read_valid[eb] = true;
           ld->skip_rows(rows);
           b.direct = true;
           b.gathered.store(static_cast<uint32_t>(rows), std::memory_order_release);
@@ -720,6 +731,7 @@ int dm_fexec_destroy(void* h) {
     cudaEventDestroy(b.done);
   }
   cudaEventDestroy(ex->last_done);
+  for (auto& e : ex->feed_read) cudaEventDestroy(e);
   cudaEventDestroy(ex->t_start);
   cudaEventDestroy(ex->t_stop);
   cudaFree(ex->x_dev);
