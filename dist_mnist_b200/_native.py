@@ -238,6 +238,7 @@ def _declare(l: C.CDLL) -> None:
         "dm_loader_destroy": (None, [vp]),
         "dm_loader_enable_feed": (i, [vp, vp, vp, vp, vp, i]),
         "dm_loader_feed_enabled": (i, [vp]),
+        "dm_copy_row_streaming": (None, [vp, vp, sz]),
         "dm_exec_create": (i, [i, i, i, i, sz, sz, C.POINTER(vp)]),
         "dm_exec_capture_stream": (vp, [vp, i]),
         "dm_exec_graph_steps": (i, [vp]),

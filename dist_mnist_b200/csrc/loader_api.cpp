@@ -9,7 +9,43 @@
 #include "loader.h"
 #include "trace.h"
 
+#if defined(__x86_64__) && !defined(__SANITIZE_THREAD__)
+#include <immintrin.h>
+#define DM_STREAMING_COPY 1
+#endif
+
 using dm::BatchLoader;
+
+namespace dm {
+
+#ifdef DM_STREAMING_COPY
+namespace {
+__attribute__((target("avx2"))) void copy_nt_avx2(uint8_t* dst, const uint8_t* src, size_t n) {   // dst 32 B aligned, n % 32 == 0
+  for (size_t i = 0; i < n; i += 32)
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i)));
+}
+void copy_nt_sse2(uint8_t* dst, const uint8_t* src, size_t n) {   // dst 16 B aligned, n % 16 == 0
+  for (size_t i = 0; i < n; i += 16)
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i)));
+}
+const bool g_have_avx2 = __builtin_cpu_supports("avx2");
+}  // namespace
+
+void copy_row_streaming(uint8_t* dst, const uint8_t* src, size_t n) {
+  const uintptr_t d = reinterpret_cast<uintptr_t>(dst);
+  if (n < 256) { memcpy(dst, src, n); return; }   // short rows: not worth bypassing the cache
+  if (g_have_avx2 && (d & 31) == 0 && (n & 31) == 0) copy_nt_avx2(dst, src, n);
+  else if ((d & 15) == 0 && (n & 15) == 0) copy_nt_sse2(dst, src, n);
+  else memcpy(dst, src, n);
+}
+void streaming_fence() { _mm_sfence(); }
+#else
+// (ThreadSanitizer builds and non-x86 hosts: plain copies — TSan does not see streaming stores)
+void copy_row_streaming(uint8_t* dst, const uint8_t* src, size_t n) { memcpy(dst, src, n); }
+void streaming_fence() {}
+#endif
+
+}  // namespace dm
 
 extern "C" {
 
@@ -38,6 +74,12 @@ void dm_loader_next(void* h, void* x_dst, void* y_dst) {
 
 uint64_t dm_loader_epochs(void* h) { return static_cast<BatchLoader*>(h)->epochs; }
 
+// Test hook: the streaming row copy on its own (any size / alignment must equal memcpy).
+void dm_copy_row_streaming(void* dst, const void* src, size_t n) {
+  dm::copy_row_streaming(static_cast<uint8_t*>(dst), static_cast<const uint8_t*>(src), n);
+  dm::streaming_fence();
+}
+
 // Epoch feed (loader.h): x0/y0/x1/y1 are two pairs of caller-owned pinned buffers of n rows each (x_row_bytes /
 // y_row_bytes per row, densely packed). Fills the current epoch's buffer here (a few helper threads; ~170 MB for MNIST)
 // and returns 1; returns 0 and leaves the loader unchanged when the layout does not allow contiguous slices
@@ -63,9 +105,11 @@ int dm_loader_enable_feed(void* h, void* x0, void* y0, void* x1, void* y1, int n
     if (r0 >= r1) break;
     th.emplace_back([l, idx, b, r0, r1] {
       for (size_t r = r0; r < r1; ++r) {
-        memcpy(l->feed_x[b] + r * l->x_row_bytes, l->images + static_cast<size_t>(idx[r]) * l->x_row_bytes, l->x_row_bytes);
+        dm::copy_row_streaming(l->feed_x[b] + r * l->x_row_bytes, l->images + static_cast<size_t>(idx[r]) * l->x_row_bytes,
+                               l->x_row_bytes);
         memcpy(l->feed_y[b] + r * l->y_row_bytes, l->labels + static_cast<size_t>(idx[r]) * l->y_row_bytes, l->y_row_bytes);
       }
+      dm::streaming_fence();
     });
   }
   for (auto& t : th) t.join();

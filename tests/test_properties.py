@@ -1,7 +1,7 @@
 """Property tests (hypothesis): arena layout / item tiling for arbitrary MLP shapes, and the native next_batch
 loader against an independent model of TF's `DataSet.next_batch` for arbitrary dataset / batch sizes."""
 import torch
-from hypothesis import given, settings, strategies as st
+from hypothesis import example, given, settings, strategies as st
 
 from dist_mnist_b200 import _native as N
 from dist_mnist_b200.models.mlp import MLPSpec
@@ -103,3 +103,29 @@ def test_fused_tiling_any_eligible_model(in_chunks, in_tail, hidden, classes, nu
         assert [s.ps for s in sl] == [r % num_ps for r in range(8)]
     else:
         assert len({s.ps for s in sl}) == 1
+
+
+@settings(max_examples=150, deadline=None)
+@given(n=st.integers(min_value=0, max_value=5000), dst_off=st.integers(min_value=0, max_value=63),
+       src_off=st.integers(min_value=0, max_value=63))
+@example(n=3136, dst_off=0, src_off=0)      # an MNIST fp32 row, 32-byte aligned: the AVX2 loop
+@example(n=3136, dst_off=32, src_off=5)
+@example(n=3136, dst_off=16, src_off=3)     # 16-byte aligned only: the SSE2 loop
+@example(n=4096, dst_off=0, src_off=1)
+@example(n=256, dst_off=0, src_off=0)
+@example(n=272, dst_off=48, src_off=7)
+@example(n=3140, dst_off=0, src_off=0)      # size not a multiple of 16: memcpy fallback
+def test_streaming_row_copy_equals_memcpy_for_any_size_and_alignment(n, dst_off, src_off):
+    """loader.h copy_row_streaming (non-temporal stores with AVX2 / SSE2 fast paths and a memcpy fallback) must be a
+    plain copy for every size and alignment, and must not touch a byte outside [dst, dst + n)."""
+    import numpy as np
+    from dist_mnist_b200 import _native as N
+    lib = N.lib()
+    src = np.random.default_rng(n * 4096 + dst_off * 64 + src_off).integers(0, 256, size=n + 128, dtype=np.uint8)
+    dst = np.full(n + 192, 0xA5, dtype=np.uint8)
+    base_d = dst.ctypes.data
+    pad = (-base_d) % 64                       # start from a 64-byte aligned address, then apply the offset
+    lib.dm_copy_row_streaming(base_d + pad + dst_off, src.ctypes.data + src_off, n)
+    lo = pad + dst_off
+    assert np.array_equal(dst[lo:lo + n], src[src_off:src_off + n])
+    assert (dst[:lo] == 0xA5).all() and (dst[lo + n:] == 0xA5).all()
