@@ -3,6 +3,8 @@
 //
 // Reference: `mnist.train.next_batch(32)` (/root/reference/distributed_server-basic.py:111) on TF's DataSet: shuffle
 // at every epoch boundary, sequential batches, a batch that straddles the boundary is completed from the next epoch.
+#include <stdlib.h>
+
 #include <chrono>
 #include <thread>
 
@@ -29,11 +31,12 @@ void copy_nt_sse2(uint8_t* dst, const uint8_t* src, size_t n) {   // dst 16 B al
     _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i)));
 }
 const bool g_have_avx2 = __builtin_cpu_supports("avx2");
+const bool g_streaming = [] { const char* e = getenv("DM_STREAMING_COPY"); return e == nullptr || e[0] != '0'; }();   // A/B knob
 }  // namespace
 
 void copy_row_streaming(uint8_t* dst, const uint8_t* src, size_t n) {
   const uintptr_t d = reinterpret_cast<uintptr_t>(dst);
-  if (n < 256) { memcpy(dst, src, n); return; }   // short rows: not worth bypassing the cache
+  if (n < 256 || !g_streaming) { memcpy(dst, src, n); return; }   // short rows: not worth bypassing the cache
   if (g_have_avx2 && (d & 31) == 0 && (n & 31) == 0) copy_nt_avx2(dst, src, n);
   else if ((d & 15) == 0 && (n & 15) == 0) copy_nt_sse2(dst, src, n);
   else memcpy(dst, src, n);
