@@ -47,3 +47,9 @@ def test_toy_parameter_server_round_trip():
         except subprocess.TimeoutExpired:
             ps.kill()
         ps.communicate()
+
+
+def test_nvls_probe_example_reports_cleanly_without_gpus():
+    # no GPU here: the probe must say why it cannot run and exit non-zero instead of crashing
+    r = _run("nvls_multicast_probe.py", "2")
+    assert r.returncode == 1 and "PROBE FAILED" in r.stdout and "FAIL:" in r.stdout, (r.stdout, r.stderr)
