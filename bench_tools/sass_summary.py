@@ -48,9 +48,13 @@ def main() -> int:
             flush_listing()
             cur_name, cur_lines = m.group(1), []
             continue
+        if cur_name and (line.strip().startswith("....") or line.startswith("Fatbin elf code")):
+            flush_listing()          # end of this cubin: what follows is the next ELF's header, not this kernel
+            cur_name, cur_lines = None, []
+            continue
         if cur_name:
             # keep the instruction text, drop the encoding words (halves the size, loses nothing readable)
-            mm = re.match(r"(\s+/\*[0-9a-f]{4}\*/\s+.*?;)\s+/\* 0x[0-9a-f]+ \*/", line)
+            mm = re.match(r"(\s+/\*[0-9a-f]{4,8}\*/\s+.*?;)\s+/\* 0x[0-9a-f]+ \*/", line)
             if mm:
                 cur_lines.append(mm.group(1))
             elif re.match(r"\s+/\* 0x[0-9a-f]+ \*/\s*$", line):
@@ -73,7 +77,7 @@ def main() -> int:
             flush()
             name, counts, n = m.group(1), collections.Counter(), 0
             continue
-        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        m = re.match(r"\s+/\*[0-9a-f]{4,8}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
         if m and name:
             n += 1
             op = m.group(1)
