@@ -188,3 +188,27 @@ def test_more_ps_tasks_than_variables_global_step_and_exit():
         while any(p.kernel_running() for p in cl.ps):
             assert time.time() - t0 < 20, "a ps shard (the item-less one?) did not exit after every worker was done"
             time.sleep(0.01)
+
+
+@pytest.mark.timeout(180)
+def test_two_ps_row_split_two_workers_processes():
+    """`--ps_hosts` is a list in the reference (DS:73-77); with `--sharding row_split` the hidden weight itself is
+    split over both ps processes, so every push of every worker goes to two shards. The exit lines give the counters:
+    the shard that owns the step counter must have seen exactly the sum of the workers' steps."""
+    ps_hosts = f"127.0.0.1:{_free_port()},127.0.0.1:{_free_port()}"
+    worker_hosts = f"127.0.0.1:{_free_port()},127.0.0.1:{_free_port()}"
+    common = ["--train_steps", "240", "--learning_rate", "0.001", "--sharding", "row_split"]
+    ps0 = _spawn("ps", 0, ps_hosts, worker_hosts, common + ["--ps_exit_when_done"])
+    ps1 = _spawn("ps", 1, ps_hosts, worker_hosts, common + ["--ps_exit_when_done"])
+    time.sleep(0.5)
+    w1 = _spawn("worker", 1, ps_hosts, worker_hosts, common)
+    w0 = _spawn("worker", 0, ps_hosts, worker_hosts, common)
+    out0, out1 = _finish(w0, 120), _finish(w1, 120)
+    outp0, outp1 = _finish(ps0, 60), _finish(ps1, 60)
+    for p, o in ((w0, out0), (w1, out1), (ps0, outp0), (ps1, outp1)):
+        assert p.returncode == 0, o
+    done = [int(l.split("local_steps=")[1].split()[0].rstrip(",")) for l in (out0 + out1).splitlines() if "local_steps=" in l]
+    assert len(done) == 2 and sum(done) >= 240
+    gsteps = [int(l.split("global_step=")[1].split()[0].rstrip(",")) for l in (outp0 + outp1).splitlines()
+              if "exiting: global_step=" in l]
+    assert gsteps and max(gsteps) == sum(done), (gsteps, done)
