@@ -28,3 +28,27 @@ def test_native_library_carries_nvtx_ranges():
     for name in ("dm.fexec.run", "dm.fexec.chunk.launch", "dm.exec.run", "dm.loader.enable_feed"):
         assert name in out, name
     assert os.path.exists(so)
+
+
+def test_clock_csv_summary_reports_median_clock_and_throttle_reasons():
+    """The `clocks` object of the bench JSON line: median SM clock under load, max clock, and every throttle reason that
+    was active in any sample (hw_slowdown / thermal reasons reject a run; sw_power_cap is kept and noted)."""
+    csv_text = "\n".join([
+        "0, 1965, 1965, 412.31, 0x0000000000000000, Not Active, Not Active, Not Active, Not Active",
+        "0, 1965, 1965, 640.02, 0x0000000000000004, Not Active, Not Active, Not Active, Active",
+        "0, 1920, 1965, 998.70, 0x0000000000000004, Not Active, Not Active, Not Active, Active",
+        "1, 1965, 1965, 120.00, 0x0000000000000000, Not Active, Not Active, Not Active, Not Active",
+        "0, [N/A], [N/A], [N/A], [N/A], [N/A], [N/A], [N/A], [N/A]",     # a sample taken while the driver was busy
+        "garbage line",
+    ])
+    s = metrics.summarize_clock_csv(csv_text)
+    assert s["samples"] == 4 and s["sm_mhz"] == 1965 and s["sm_max_mhz"] == 1965
+    assert s["reasons"] == ["sw_power_cap"] and abs(s["power_w_max"] - 998.70) < 1e-6
+    hot = metrics.summarize_clock_csv("0, 1200, 1965, 700.0, 0x8, Active, Active, Not Active, Not Active\n")
+    assert hot["reasons"] == ["hw_slowdown", "hw_thermal_slowdown"] and hot["sm_mhz"] == 1200
+    assert metrics.summarize_clock_csv("")["samples"] == 0
+    # without nvidia-smi the sampler is a no-op that still returns the same shape
+    sampler = metrics.ClockSampler(interval_ms=10)
+    sampler.start()
+    out = sampler.stop()
+    assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples"}
