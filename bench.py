@@ -110,6 +110,14 @@ def main(argv=None) -> int:
         print(json.dumps({"impl": "reference", "unavailable": REFERENCE_UNAVAILABLE}))
         return 0
 
+    # Hang watchdog: a healthy run takes seconds to a couple of minutes (the first `import torch` on a fresh box
+    # included). If something deadlocks, dump every Python thread's stack to stderr and exit instead of sitting in the
+    # caller's timeout without a trace. DM_BENCH_WATCHDOG_S=0 switches it off.
+    import faulthandler
+    watchdog_s = int(os.environ.get("DM_BENCH_WATCHDOG_S", "1500"))
+    if watchdog_s > 0:
+        faulthandler.dump_traceback_later(watchdog_s, exit=True)
+
     import torch.distributed as dist
 
     from dist_mnist_b200 import _native as N
@@ -488,6 +496,7 @@ def main(argv=None) -> int:
         for ps in ps_list:
             ps.close()
         dist.destroy_process_group()
+    faulthandler.cancel_dump_traceback_later()
     return 0
 
 
