@@ -222,6 +222,7 @@ struct FusedExec {
   uint64_t steps_done = 0;    // steps completed over the executor's lifetime == push sequence numbers used
   uint64_t launches = 0;
   uint64_t direct_chunks = 0, gathered_chunks = 0, fills_posted = 0;   // feed statistics (dm_fexec_feed_stats)
+  bool feed_broken = false;   // a copy out of an epoch buffer was refused: this executor stays on the row-gather path
   ChunkBuf bufs[kBuffers];
   GatherPool pool;
   cudaEvent_t feed_read[2] = {nullptr, nullptr};     // epoch feed: last H2D copy that reads epoch buffer b (copy stream)
@@ -486,8 +487,8 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
     }
   }
   // epoch feed usable with this executor's ring geometry: a slot is exactly one dense batch
-  const bool feed_ok = ld->feed && ld->batch == kRowsPerSlot &&
-                       ld->x_row_bytes * kRowsPerSlot == ex->x_slot_bytes && ld->y_row_bytes * kRowsPerSlot == ex->y_slot_bytes;
+  bool feed_ok = ld->feed && !ex->feed_broken && ld->batch == kRowsPerSlot &&
+                 ld->x_row_bytes * kRowsPerSlot == ex->x_slot_bytes && ld->y_row_bytes * kRowsPerSlot == ex->y_slot_bytes;
   const size_t nchunks = sizes.size();
   std::vector<uint64_t> first(nchunks + 1, 0);
   for (size_t c = 0; c < nchunks; ++c) first[c + 1] = first[c] + sizes[c];
@@ -565,17 +566,29 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
                                 rows * ld->y_row_bytes, cudaMemcpyHostToDevice, ex->copy);
           if (e == cudaSuccess) e = cudaEventRecord(b.copied, ex->copy);
           if (e == cudaSuccess) e = cudaEventRecord(ex->feed_read[eb], ex->copy);
-          if (e != cudaSuccess) { rc = fxfail("chunk transfer (epoch feed)", e); break; }
-          ex->feed_read_valid[eb] = true;
-          ld->skip_rows(rows);
-          b.direct = true;
-          b.gathered.store(static_cast<uint32_t>(rows), std::memory_order_release);
-          ++ex->direct_chunks;
-          ++next_gather;
-          // nothing to wait for: launch what is planned before planning further ahead (the copies of the following
-          // chunk are enqueued right after this chunk's launch and still overlap its kernel); planning three chunks
-          // ahead first would only delay the first launch of a short run by the host time of six copy calls
-          break;
+          if (e == cudaSuccess) {
+            ex->feed_read_valid[eb] = true;
+            ld->skip_rows(rows);
+            b.direct = true;
+            b.gathered.store(static_cast<uint32_t>(rows), std::memory_order_release);
+            ++ex->direct_chunks;
+            ++next_gather;
+            // nothing to wait for: launch what is planned before planning further ahead (the copies of the following
+            // chunk are enqueued right after this chunk's launch and still overlap its kernel); planning three chunks
+            // ahead first would only delay the first launch of a short run by the host time of six copy calls
+            break;
+          }
+          // The runtime refused a copy out of the epoch buffer (a synchronous, non-sticky error: nothing was consumed
+          // from the loader yet). Training must not die of an input-path optimisation: say so once, stay on the
+          // row-gather path from here on — this chunk included (its ring slots are simply copied again, in order, on
+          // the same stream).
+          fprintf(stderr, "[dm] fused executor: epoch feed switched off (%s: %s); using the row-gather path\n",
+                  cudaGetErrorName(e), cudaGetErrorString(e));
+          cudaGetLastError();
+          ex->feed_broken = true;
+          ex->feed_read_valid[eb] = true;   // (conservative: an x copy may have been enqueued before the failure)
+          cudaEventRecord(ex->feed_read[eb], ex->copy);
+          feed_ok = false;
         }
       }
       ++ex->gathered_chunks;

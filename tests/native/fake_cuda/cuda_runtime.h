@@ -177,7 +177,14 @@ inline cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned) 
   });
   return cudaSuccess;
 }
+namespace fakecuda {
+// Fault injection: copies whose source the predicate selects are refused (synchronous cudaErrorInvalidValue) after
+// `countdown` such copies have been let through.
+inline std::function<bool(const void*)>& fail_pred() { static std::function<bool(const void*)> f; return f; }
+inline int& fail_countdown() { static int n = 0; return n; }
+}  // namespace fakecuda
 inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind, cudaStream_t s) {
+  if (fakecuda::fail_pred() && fakecuda::fail_pred()(src) && fakecuda::fail_countdown()-- <= 0) return cudaErrorInvalidValue;
   s->push([dst, src, n] {
     fakecuda::random_delay();
     memcpy(dst, src, n);   // the source is read now, not when the copy was enqueued

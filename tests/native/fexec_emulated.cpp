@@ -97,6 +97,17 @@ int main(int argc, char** argv) {
     const int en = dm_loader_enable_feed(ld, fx[0].data(), fy[0].data(), fx[1].data(), fy[1].data(), 3);
     CHECK(en == (n >= 1024 ? 1 : 0));
   }
+  if (const char* e = getenv("FAKE_FAIL_FEED_COPY")) {   // refuse copies out of the epoch buffers after `e` good ones
+    fakecuda::fail_countdown() = atoi(e);
+    fakecuda::fail_pred() = [&](const void* src) {
+      for (int b = 0; b < 2; ++b) {
+        const char* p = static_cast<const char*>(src);
+        if (!fx[b].empty() && p >= reinterpret_cast<const char*>(fx[b].data()) && p < reinterpret_cast<const char*>(fx[b].data() + fx[b].size())) return true;
+        if (!fy[b].empty() && p >= reinterpret_cast<const char*>(fy[b].data()) && p < reinterpret_cast<const char*>(fy[b].data() + fy[b].size())) return true;
+      }
+      return false;
+    };
+  }
   void* ex = nullptr;
   CHECK(dm_fexec_create(0, 4, I, C, B, &ex) == 0);
   void *xd, *yd, *xs, *ys, *ctl;

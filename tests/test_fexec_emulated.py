@@ -42,9 +42,9 @@ def harness_tsan(tmp_path_factory):
     return _build(tmp_path_factory, ["-fsanitize=thread"])
 
 
-def run(exe, n, feed, steps, delay_us=50, threads=3, seed=0):
+def run(exe, n, feed, steps, delay_us=50, threads=3, seed=0, extra_env=None):
     env = dict(os.environ, FAKE_CUDA_DELAY_US=str(delay_us), DM_GATHER_THREADS=str(threads),
-               ASAN_OPTIONS="detect_leaks=1")
+               ASAN_OPTIONS="detect_leaks=1", **(extra_env or {}))
     r = subprocess.run([exe, str(n), str(feed), str(steps), str(seed)], capture_output=True, text=True, env=env,
                        timeout=600)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
@@ -95,3 +95,11 @@ def test_random_geometries(harness):
         s = run(harness, n, 1, rnd.randint(300, 900), delay_us=rnd.choice([0, 20, 150]), threads=rnd.choice([1, 2, 4]),
                 seed=rnd.randint(1, 10 ** 6))
         assert int(s["direct_chunks"]) > 0
+
+
+@pytest.mark.parametrize("good_copies", [0, 1, 7, 40])
+def test_a_refused_epoch_buffer_copy_falls_back_to_the_row_gather(harness, good_copies):
+    # the runtime refuses a copy out of the epoch buffer (x or labels) after `good_copies` such copies went through:
+    # the executor must say so, stay on the gather path and still hand every step exactly its batch
+    s = run(harness, 3000, 1, 900, extra_env={"FAKE_FAIL_FEED_COPY": str(good_copies)})
+    assert int(s["direct_chunks"]) <= good_copies // 2 + 1 and int(s["gathered_chunks"]) > 60
