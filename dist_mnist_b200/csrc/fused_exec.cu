@@ -553,8 +553,15 @@ int dm_fexec_run(void* h, void* loader, uint64_t n_steps, void* out_results, uin
         const size_t rows = static_cast<size_t>(sizes[c]) * ld->batch;
         // the current epoch's buffer is still being filled (start of a run right after a boundary, or the consumer
         // is faster than the helpers): help finishing it — cheaper than gathering the same rows batch by batch
-        while (ld->cursor + rows <= ld->n && ld->feed_fill_in_progress()) {
-          if (!ex->pool.fill_step()) cpu_relax();
+        if (ld->cursor + rows <= ld->n && ld->feed_fill_in_progress()) {
+          const auto t_wait = std::chrono::steady_clock::now();
+          while (ld->feed_fill_in_progress()) {
+            if (ex->pool.fill_step()) continue;
+            cpu_relax();
+            // (all blocks are claimed, the last ones are in flight on helper threads: microseconds. The deadline only
+            // keeps a stuck helper from stalling training — the chunk then takes the gather path.)
+            if (std::chrono::steady_clock::now() - t_wait > std::chrono::seconds(2)) break;
+          }
         }
         if (maybe_post_fill(ex, ld) != 0) { rc = -1; break; }
         if (ld->feed_slice_ready(rows)) {
