@@ -43,8 +43,10 @@ def save_checkpoint(worker, directory: str) -> str:
     tmp = path + ".tmp"
     torch.save(state, tmp)
     os.replace(tmp, path)
-    with open(os.path.join(directory, "checkpoint"), "w") as f:
+    index = os.path.join(directory, "checkpoint")   # TF-style index file, replaced atomically like the checkpoint itself
+    with open(index + ".tmp", "w") as f:
         f.write(f'model_checkpoint_path: "{name}"\n')
+    os.replace(index + ".tmp", index)
     return path
 
 
