@@ -84,3 +84,14 @@ def test_adam_math_flag_selects_the_ieee_ps_kernel():
     if shutil.which("cuobjdump"):
         syms = subprocess.run(["cuobjdump", "-elf", str(N.lib_path())], capture_output=True, text=True).stdout
         assert "ps_serve_kernelILb0EE" in syms and "ps_serve_kernelILb1EE" in syms
+
+
+def test_package_is_runnable_as_a_module():
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "dist_mnist_b200", "--job_name", "", "--backend", "cpu"], capture_output=True,
+                       text=True, cwd=root, env=dict(os.environ, PYTHONPATH=root))
+    # same validation as the reference (DS:61-62): an empty job name is an error before anything else happens
+    assert r.returncode != 0 and "Must specify the job name explicitly" in (r.stdout + r.stderr)
