@@ -48,9 +48,10 @@ __global__ void unicast_publish_kernel(const float4* __restrict__ src, float4* c
   __threadfence_system();
 }
 
-// In-switch reduction: one `multimem.ld_reduce` returns the SUM over the replicas of every GPU of the team. This is the
-// sync-replicas aggregation (SyncReplicasOptimizer, /root/reference/distributed_server-basic.py:66-71) done by the
-// NVSwitch instead of the ps: the ps reads each aggregated gradient element once instead of once per worker.
+// In-switch reduction: one `multimem.ld_reduce` returns the SUM over the replicas of every GPU of the team — the
+// gradient aggregation of a merged / synchronous apply (`--apply_mode merged`; the reference itself only has the
+// asynchronous per-push apply, /root/reference/distributed_server-basic.py:102-103) done by the NVSwitch instead of
+// the ps: the ps reads each aggregated gradient element once instead of once per worker.
 __global__ void multimem_reduce_kernel(const float4* mc_src, float4* __restrict__ out, size_t n4) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
