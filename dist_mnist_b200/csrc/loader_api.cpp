@@ -30,7 +30,7 @@ void copy_nt_sse2(uint8_t* dst, const uint8_t* src, size_t n) {   // dst 16 B al
   for (size_t i = 0; i < n; i += 16)
     _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i)));
 }
-const bool g_have_avx2 = __builtin_cpu_supports("avx2");
+const bool g_have_avx2 = [] { __builtin_cpu_init(); return __builtin_cpu_supports("avx2") != 0; }();
 const bool g_streaming = [] { const char* e = getenv("DM_STREAMING_COPY"); return e == nullptr || e[0] != '0'; }();   // A/B knob
 }  // namespace
 
