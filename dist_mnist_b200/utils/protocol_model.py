@@ -164,6 +164,47 @@ def check(cfg: Config, max_states: int = 2_000_000) -> Result:
     return Result(True, len(parent))
 
 
+def simulate(cfg: Config, seed: int, bias: str = "uniform", max_moves: int = 10_000_000) -> Result:
+    """One random schedule of a configuration that is too large to enumerate (the production default is 12 lanes x 48
+    slots). `bias` skews the scheduler: "uniform", "slow_ps" (the ps moves only when nothing else can or with 2 %
+    probability: maximal back-pressure), "slow_lane" (lane 0 is starved the same way: a straggler holding an old
+    sequence number), "fast_ps". Same checks as `check`."""
+    import random
+    rnd = random.Random(seed)
+    st = _initial(cfg)
+    moves = 0
+    while moves < max_moves:
+        succ = _successors(cfg, st)
+        counter, ack, ps_next, published, slots, lanes = st
+        if not succ:
+            if ack == cfg.n_steps and all(l[0] == DONE for l in lanes):
+                return Result(True, moves)
+            return Result(False, moves, f"deadlock after {moves} moves: ack={ack}, ps waits for push {ps_next}")
+        pick = None
+        if bias != "uniform" and len(succ) > 1:
+            slow = "ps applies" if bias == "slow_ps" else "lane 0 " if bias == "slow_lane" else None
+            fast = "ps applies" if bias == "fast_ps" else None
+            if slow is not None and rnd.random() > 0.02:
+                others = [x for x in succ if not x[0].startswith(slow)]
+                if others:
+                    pick = rnd.choice(others)
+            if fast is not None:
+                f = [x for x in succ if x[0].startswith(fast)]
+                if f and rnd.random() < 0.9:
+                    pick = f[0]
+        if pick is None:
+            pick = rnd.choice(succ)
+        label, st, err = pick
+        if err:
+            return Result(False, moves, err)
+        # the set of published-and-applied pushes is never consulted again: keep the state small
+        counter, ack, ps_next, published, slots, lanes = st
+        if len(published) > 4 * cfg.nslots:
+            st = (counter, ack, ps_next, frozenset(x for x in published if x >= ps_next), slots, lanes)
+        moves += 1
+    return Result(False, moves, "move limit exceeded")
+
+
 def main() -> int:   # python -m dist_mnist_b200.utils.protocol_model LANES NSLOTS STEPS [noguard]
     import sys
     a = sys.argv[1:]

@@ -45,3 +45,20 @@ def test_engine_config_keeps_the_ring_at_least_as_deep_as_the_lanes():
     # the model's precondition nslots >= lanes is what EngineConfig.validate enforces for the real engine
     with pytest.raises(ValueError):
         EngineConfig(backend="cpu", lanes=4, nslots=2).validate(OptimizerConfig("adam", 1e-4))
+
+
+@pytest.mark.parametrize("lanes,nslots", [(12, 48), (12, 12), (8, 16), (4, 8), (16, 64)])
+def test_random_schedules_of_production_sized_configurations(lanes, nslots):
+    """The CLI / bench default (12 lanes, 48 mailbox slots) is far too large to enumerate: random schedules, also with a
+    starved ps (maximal back-pressure on the flow control), a straggling lane (holds an old sequence number while the
+    others race ahead) and an eager ps."""
+    from dist_mnist_b200.utils.protocol_model import simulate
+
+    for bias in ("uniform", "slow_ps", "slow_lane", "fast_ps"):
+        for seed in range(6):
+            r = simulate(Config(lanes, nslots, 400), seed, bias)
+            assert r.ok, (bias, seed, r.reason)
+    # and the unguarded variant is caught by random schedules too (it deadlocks as soon as a lane's next claim is
+    # >= nslots ahead of its deferred push)
+    bad = [simulate(Config(lanes, nslots, 400, guard=False), seed, "slow_lane") for seed in range(6)]
+    assert any(not r.ok and r.reason.startswith("deadlock") for r in bad) or lanes < 4
