@@ -42,6 +42,8 @@ class Config:
     guard: bool = True        # the kernel's deferral guard (nxt - cur) < nslots // 2
     defer: bool = True        # deferred publishing at all (False: publish right after the push)
     strict: bool = False      # --strict_steps: publish at once and wait for the acknowledgement before the next step
+    shards: int = 1           # ps tasks the worker pushes to (row_split: every push has a tile on every shard); each
+                              # shard consumes and acknowledges on its own, the worker waits for the slowest
 
 
 @dataclass
@@ -52,7 +54,8 @@ class Result:
     trace: Optional[List[str]] = None
 
 
-# state = (counter, ack, ps_next, published(frozenset), slots(tuple), lanes(tuple of (phase, cur, nxt, pend)))
+# state = (counter, acks(per shard), ps_next(per shard), published(frozenset), slots(tuple),
+#          lanes(tuple of (phase, cur, nxt, pend)))
 def _initial(cfg: Config):
     lanes = []
     counter = 0
@@ -62,24 +65,30 @@ def _initial(cfg: Config):
             counter += 1
         else:
             lanes.append((DONE, -1, -1, -1))
-    return (counter, 0, 1, frozenset(), tuple([0] * cfg.nslots), tuple(lanes))
+    return (counter, tuple([0] * cfg.shards), tuple([1] * cfg.shards), frozenset(), tuple([0] * cfg.nslots), tuple(lanes))
 
 
 def _successors(cfg: Config, st) -> List[Tuple[str, tuple, Optional[str]]]:
-    counter, ack, ps_next, published, slots, lanes = st
+    counter, acks, ps_nexts, published, slots, lanes = st
+    ack = min(acks)          # what the worker's flow control / strict wait sees: the slowest shard
+    ps_next = min(ps_nexts)
     out = []
-    # ---- ps: apply the next push of this worker if it has been published ----
-    if ps_next in published:
-        err = None
-        if slots[ps_next % cfg.nslots] != ps_next:
-            err = f"ps reads slot {ps_next % cfg.nslots} for push {ps_next} but it holds push {slots[ps_next % cfg.nslots]}"
-        out.append((f"ps applies {ps_next}", (counter, ps_next, ps_next + 1, published, slots, lanes), err))
+    # ---- ps shards: each applies the next push of this worker once it has been published ----
+    for k in range(cfg.shards):
+        nk = ps_nexts[k]
+        if nk in published:
+            err = None
+            if slots[nk % cfg.nslots] != nk:
+                err = f"ps {k} reads slot {nk % cfg.nslots} for push {nk} but it holds push {slots[nk % cfg.nslots]}"
+            a2 = acks[:k] + (nk,) + acks[k + 1:]
+            n2 = ps_nexts[:k] + (nk + 1,) + ps_nexts[k + 1:]
+            out.append((f"ps {k} applies {nk}" if cfg.shards > 1 else f"ps applies {nk}", (counter, a2, n2, published, slots, lanes), err))
     # ---- lanes ----
     for i, (phase, cur, nxt, pend) in enumerate(lanes):
         def put(new_lane, **kw):
             l2 = list(lanes)
             l2[i] = new_lane
-            return (kw.get("counter", counter), ack, ps_next, kw.get("published", published), kw.get("slots", slots),
+            return (kw.get("counter", counter), acks, ps_nexts, kw.get("published", published), kw.get("slots", slots),
                     tuple(l2))
         seq = cur + 1
         if phase == CLAIM:       # prologue: claim the lane's next step
@@ -144,7 +153,8 @@ def check(cfg: Config, max_states: int = 2_000_000) -> Result:
     while q:
         st = q.popleft()
         succ = _successors(cfg, st)
-        counter, ack, ps_next, published, slots, lanes = st
+        counter, acks, ps_nexts, published, slots, lanes = st
+        ack, ps_next = min(acks), min(ps_nexts)
         if not succ:
             if ack == cfg.n_steps and all(l[0] == DONE for l in lanes):
                 continue   # proper termination
@@ -175,15 +185,16 @@ def simulate(cfg: Config, seed: int, bias: str = "uniform", max_moves: int = 10_
     moves = 0
     while moves < max_moves:
         succ = _successors(cfg, st)
-        counter, ack, ps_next, published, slots, lanes = st
+        counter, acks, ps_nexts, published, slots, lanes = st
+        ack, ps_next = min(acks), min(ps_nexts)
         if not succ:
             if ack == cfg.n_steps and all(l[0] == DONE for l in lanes):
                 return Result(True, moves)
             return Result(False, moves, f"deadlock after {moves} moves: ack={ack}, ps waits for push {ps_next}")
         pick = None
         if bias != "uniform" and len(succ) > 1:
-            slow = "ps applies" if bias == "slow_ps" else "lane 0 " if bias == "slow_lane" else None
-            fast = "ps applies" if bias == "fast_ps" else None
+            slow = "ps " if bias == "slow_ps" else "lane 0 " if bias == "slow_lane" else None
+            fast = "ps " if bias == "fast_ps" else None
             if slow is not None and rnd.random() > 0.02:
                 others = [x for x in succ if not x[0].startswith(slow)]
                 if others:
@@ -198,9 +209,9 @@ def simulate(cfg: Config, seed: int, bias: str = "uniform", max_moves: int = 10_
         if err:
             return Result(False, moves, err)
         # the set of published-and-applied pushes is never consulted again: keep the state small
-        counter, ack, ps_next, published, slots, lanes = st
+        counter, acks, ps_nexts, published, slots, lanes = st
         if len(published) > 4 * cfg.nslots:
-            st = (counter, ack, ps_next, frozenset(x for x in published if x >= ps_next), slots, lanes)
+            st = (counter, acks, ps_nexts, frozenset(x for x in published if x >= min(ps_nexts)), slots, lanes)
         moves += 1
     return Result(False, moves, "move limit exceeded")
 
@@ -208,7 +219,8 @@ def simulate(cfg: Config, seed: int, bias: str = "uniform", max_moves: int = 10_
 def main() -> int:   # python -m dist_mnist_b200.utils.protocol_model LANES NSLOTS STEPS [noguard]
     import sys
     a = sys.argv[1:]
-    cfg = Config(int(a[0]), int(a[1]), int(a[2]), guard="noguard" not in a, strict="strict" in a)
+    shards = next((int(x.split("=")[1]) for x in a if x.startswith("shards=")), 1)
+    cfg = Config(int(a[0]), int(a[1]), int(a[2]), guard="noguard" not in a, strict="strict" in a, shards=shards)
     r = check(cfg)
     print(cfg, "->", "OK" if r.ok else "FAILED: " + r.reason, f"({r.states} states)")
     if r.trace:

@@ -62,3 +62,14 @@ def test_random_schedules_of_production_sized_configurations(lanes, nslots):
     # >= nslots ahead of its deferred push)
     bad = [simulate(Config(lanes, nslots, 400, guard=False), seed, "slow_lane") for seed in range(6)]
     assert any(not r.ok and r.reason.startswith("deadlock") for r in bad) or lanes < 4
+
+
+@pytest.mark.parametrize("lanes,nslots,steps,shards", [(2, 4, 7, 2), (2, 2, 6, 3), (3, 4, 6, 2), (1, 2, 6, 3)])
+def test_several_ps_shards_acknowledging_independently(lanes, nslots, steps, shards):
+    """row_split / multi-ps: every push has a part on every shard, each shard consumes and acknowledges on its own and the
+    worker's flow control waits for the slowest one."""
+    assert check(Config(lanes, nslots, steps, shards=shards)).ok
+    assert check(Config(lanes, nslots, steps, shards=shards, strict=True)).ok
+    if lanes >= 2:
+        r = check(Config(lanes, nslots, steps, shards=shards, guard=False))
+        assert not r.ok and r.reason.startswith("deadlock")
